@@ -1,0 +1,148 @@
+"""ctypes binding of libswarm_b200.so (the C ABI in include/swarm_b200.h).
+
+This is the binding a reference maintainer would add: plain pointers and
+sizes go across, torch only provides device memory and the current stream.  There is NO CPU
+fallback: if the library is missing and cannot be built, importing the env classes raises.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+_REPO = os.path.dirname(_PKG_DIR)
+LIB_PATH = os.path.join(_PKG_DIR, "libswarm_b200.so")
+SOURCES = [os.path.join(_CSRC, f) for f in ("swarm_b200.cu", "swarm_kernels.cuh", "swarm_philox.cuh")]
+HEADER = os.path.join(_REPO, "include", "swarm_b200.h")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+c_void_p, c_int, c_int32, c_int64, c_uint32, c_uint64, c_double, c_float = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
+    ctypes.c_double, ctypes.c_float)
+
+SWARM_STEP_AUTO_RESET = 1
+SWARM_STEP_CLIP_ACTIONS = 2
+SWARM_STEP_ACTIONS_F64 = 4
+
+
+class SwarmParams(ctypes.Structure):
+    _fields_ = [("n_envs", c_int32), ("n_locusts", c_int32), ("n_agents", c_int32), ("grid_size", c_int32),
+                ("n_burn_in", c_int32), ("max_episode_steps", c_int32), ("math_mode", c_int32),
+                ("reserved", c_int32),
+                ("noise", c_double), ("gravity", c_double), ("wind", c_double), ("F", c_double),
+                ("L", c_double), ("dt", c_double), ("box_width", c_double), ("box_height", c_double),
+                ("seed", c_uint64), ("env_id_offset", c_int64)]
+
+
+class SwarmState(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("xa", c_void_p), ("noise_x", c_void_p), ("noise_a", c_void_p),
+                ("elapsed", c_void_p), ("episode", c_void_p)]
+
+
+class SwarmInjectedDraws(ctypes.Structure):
+    _fields_ = [("x0", c_void_p), ("xa0", c_void_p), ("burn_actions", c_void_p),
+                ("agent_noise", c_void_p), ("particle_noise", c_void_p)]
+
+
+class SwarmStepIO(ctypes.Structure):
+    _fields_ = [("actions_f32", c_void_p), ("actions_f64", c_void_p), ("noise_a", c_void_p),
+                ("noise_x", c_void_p), ("reward", c_void_p), ("done", c_void_p), ("grid", c_void_p),
+                ("positions", c_void_p), ("v_out", c_void_p), ("flags", c_uint32), ("reserved", c_uint32)]
+
+
+# name -> (restype, argtypes); every symbol include/swarm_b200.h declares
+_P = ctypes.POINTER
+SYMBOLS = {
+    "swarm_abi_version": (c_int, []),
+    "swarm_strerror": (ctypes.c_char_p, [c_int]),
+    "swarm_last_cuda_error": (ctypes.c_char_p, []),
+    "swarm_validate": (c_int, [_P(SwarmParams)]),
+    "swarm_reset": (c_int, [_P(SwarmParams), _P(SwarmState), c_void_p, _P(SwarmInjectedDraws), c_void_p]),
+    "swarm_step": (c_int, [_P(SwarmParams), _P(SwarmState), _P(SwarmStepIO), _P(SwarmInjectedDraws), c_void_p]),
+    "swarm_step_host": (c_int, [_P(SwarmParams), _P(SwarmState), _P(SwarmStepIO), c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "swarm_rasterize": (c_int, [_P(SwarmParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "swarm_expand_obs": (c_int, [_P(SwarmParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "swarm_forces": (c_int, [_P(SwarmParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "swarm_x_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p]),
+    "swarm_xv_cutoff": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "swarm_s_potential": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p]),
+    "swarm_clip_actions": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
+    "swarm_philox_draws": (c_int, [_P(SwarmParams), _P(SwarmState), c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "swarm_philox_raw": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+}
+
+_lib = None
+
+
+class SwarmNativeError(RuntimeError):
+    pass
+
+
+def needs_build():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in SOURCES + [HEADER] if os.path.isfile(s))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/swarm_b200.cu for sm_100a into the in-tree libswarm_b200.so (nvcc cross-compiles
+    without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        raise SwarmNativeError("nvcc not found; cannot build %s" % LIB_PATH)
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, SOURCES[0]]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise SwarmNativeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
+    if verbose:
+        print(res.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def load():
+    """Load the C-ABI library (building it first if the sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        try:
+            build()
+        except SwarmNativeError:
+            if not os.path.isfile(LIB_PATH):
+                raise
+    if not os.path.isfile(LIB_PATH):
+        raise SwarmNativeError("libswarm_b200.so is missing (%s) and there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)           # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.swarm_abi_version() != 1:
+        raise SwarmNativeError("ABI version mismatch: %d" % lib.swarm_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(status, what="swarm call"):
+    if status != 0:
+        lib = load()
+        msg = lib.swarm_strerror(status).decode()
+        if status == -3:
+            msg += ": " + lib.swarm_last_cuda_error().decode()
+        raise SwarmNativeError("%s failed (%d): %s" % (what, status, msg))

@@ -1,0 +1,519 @@
+// libswarm_b200.so -- kernels + the extern "C" ABI declared in include/swarm_b200.h.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "swarm_kernels.cuh"
+
+using namespace swarm;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ kernels
+
+// SwarmEnv._step + TimeLimit + SwarmRunner auto-reset + process_state, one CTA per env.
+template <int T, bool PRECISE>
+__global__ void __launch_bounds__(512) k_step(const KP kp, const SwarmState st, const SwarmStepIO io,
+                                              const SwarmInjectedDraws dr, const int has_draws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x;
+    const int N = kp.N, A = kp.A;
+    const bool raster = io.grid != nullptr;
+    const Smem sm = carve(smem_raw, N, A, kp.G, raster);
+
+    // state -> shared memory: one double2 (LDG.128) per particle, fully coalesced
+    const double2* gx = reinterpret_cast<const double2*>(st.x) + (size_t)e * N;
+    const double2* ga = reinterpret_cast<const double2*>(st.xa) + (size_t)e * A;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.xs[i] = gx[i];
+    const double2* gna = reinterpret_cast<const double2*>(io.noise_a ? io.noise_a : st.noise_a) + (size_t)e * A;
+    for (int k = threadIdx.x; k < A; k += blockDim.x) {
+        sm.as[k] = ga[k];
+        sm.an[k] = gna[k];
+        double2 a;
+        if (io.flags & SWARM_STEP_ACTIONS_F64) {
+            a = reinterpret_cast<const double2*>(io.actions_f64)[(size_t)e * A + k];
+        } else {
+            const float2 f = reinterpret_cast<const float2*>(io.actions_f32)[(size_t)e * A + k];
+            a = make_double2((double)f.x, (double)f.y);
+        }
+        if (io.flags & SWARM_STEP_CLIP_ACTIONS) {
+            // emulator_runner.py:113-118: rows with |a| >= MAX_MOVE_NORM(1) are divided by |a|, in place
+            if (io.flags & SWARM_STEP_ACTIONS_F64) {
+                const double d = sqrt(__dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y)));
+                if (d >= 1.0) {
+                    a.x = a.x / d; a.y = a.y / d;
+                    reinterpret_cast<double2*>(io.actions_f64)[(size_t)e * A + k] = a;
+                }
+            } else {
+                const float fx = (float)a.x, fy = (float)a.y;
+                const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+                if (d >= 1.0f) {
+                    const float2 c = make_float2(__fdiv_rn(fx, d), __fdiv_rn(fy, d));
+                    reinterpret_cast<float2*>(io.actions_f32)[(size_t)e * A + k] = c;
+                    a = make_double2((double)c.x, (double)c.y);
+                }
+            }
+        }
+        sm.act[k] = a;
+    }
+    double2 nx[T];
+    {
+        const double2* gnx = reinterpret_cast<const double2*>(io.noise_x ? io.noise_x : st.noise_x) + (size_t)e * N;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = threadIdx.x + t * blockDim.x;
+            nx[t] = j < N ? gnx[j] : make_double2(0.0, 0.0);
+        }
+    }
+    __syncthreads();
+
+    const double reward = env_step<T, PRECISE>(sm, kp, nx, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
+
+    // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
+    int elapsed = st.elapsed[e] + 1;
+    const bool done = (reward >= 0.0) || (kp.max_steps > 0 && elapsed >= kp.max_steps);
+    if (threadIdx.x == 0) {
+        io.reward[e] = (float)reward;
+        io.done[e] = done ? 1 : 0;
+    }
+    if (done && (io.flags & SWARM_STEP_AUTO_RESET)) {
+        // emulator_runner.py:127-132: the terminal reward/done are reported, the state (and
+        // therefore the observation) is the freshly reset episode's.  Block-uniform branch.
+        const uint32_t ep = st.episode[e];
+        env_reset<T, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
+        elapsed = 0;
+        if (threadIdx.x == 0) st.episode[e] = ep + 1;
+    }
+    if (threadIdx.x == 0) st.elapsed[e] = elapsed;
+
+    double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * N;
+    double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) ox[i] = sm.xs[i];
+    for (int k = threadIdx.x; k < A; k += blockDim.x) oa[k] = sm.as[k];
+
+    if (raster)
+        env_raster<T + 1>(sm, kp, io.grid + (size_t)e * kp.G * kp.G * 2, io.positions + (size_t)e * A * 2);
+}
+
+// SwarmEnv._reset for the masked envs.
+template <int T, bool PRECISE>
+__global__ void __launch_bounds__(512) k_reset(const KP kp, const SwarmState st, const uint8_t* __restrict__ mask,
+                                               const SwarmInjectedDraws dr, const int has_draws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x;
+    if (mask && !mask[e]) return;
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, false);
+    const uint32_t ep = st.episode[e];
+    env_reset<T, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
+    double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * kp.N;
+    double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * kp.A;
+    for (int i = threadIdx.x; i < kp.N; i += blockDim.x) ox[i] = sm.xs[i];
+    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) oa[k] = sm.as[k];
+    if (threadIdx.x == 0) {
+        st.elapsed[e] = 0;
+        st.episode[e] = ep + 1;
+    }
+}
+
+// SwarmStateProcessor.process_state for the batch.
+template <int T>
+__global__ void __launch_bounds__(512) k_rasterize(const KP kp, const double* __restrict__ x,
+                                                   const double* __restrict__ xa, float* __restrict__ grid,
+                                                   uint8_t* __restrict__ positions, double* __restrict__ box) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x;
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, true);
+    const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
+    const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
+    for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
+    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
+    __syncthreads();
+    env_raster<T + 1>(sm, kp, grid + (size_t)e * kp.G * kp.G * 2, positions + (size_t)e * kp.A * 2);
+    if (box && threadIdx.x == 0) {       // sm.box[0] was published before env_raster's first barrier
+        const double m = sm.box[0];
+        box[4 * e + 0] = m - kp.half_w;
+        box[4 * e + 1] = m + kp.half_w;
+        box[4 * e + 2] = 0.0;
+        box[4 * e + 3] = kp.y_hi;
+    }
+}
+
+// SwarmEnv.v_calculate for the batch (no integration).
+template <int T, bool PRECISE>
+__global__ void __launch_bounds__(512) k_forces(const KP kp, const double* __restrict__ x,
+                                                const double* __restrict__ xa, float* __restrict__ v,
+                                                float* __restrict__ reward) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x;
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, false);
+    const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
+    const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
+    for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
+    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
+    __syncthreads();
+    stage_sources(sm, kp.N, kp.A);
+    __syncthreads();
+    float vx[T], vy[T];
+    const double r = pair_forces<T, PRECISE>(sm, kp, vx, vy);
+    if (v) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = threadIdx.x + t * blockDim.x;
+            if (j < kp.N) reinterpret_cast<float2*>(v)[(size_t)e * kp.N + j] = make_float2(vx[t], vy[t]);
+        }
+    }
+    if (reward && threadIdx.x == 0) reward[e] = (float)r;
+}
+
+// SwarmRunner.get_local_states for the batch: (E,A,G,G,3) from (E,G,G,2) + (E,A,2).
+__global__ void __launch_bounds__(256) k_expand(const int E, const int A, const int G,
+                                                const float2* __restrict__ grid, const uint8_t* __restrict__ pos,
+                                                float* __restrict__ out) {
+    const int cells = G * G;
+    const int ea = blockIdx.y;             // e*A + a
+    const int e = ea / A;
+    const int hot = (int)pos[2 * ea] * G + (int)pos[2 * ea + 1];
+    const float2* g = grid + (size_t)e * cells;
+    float* o = out + (size_t)ea * cells * 3;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
+        const float2 q = __ldg(g + c);
+        __stcs(o + 3 * c + 0, q.x);
+        __stcs(o + 3 * c + 1, q.y);
+        __stcs(o + 3 * c + 2, c == hot ? 1.0f : 0.0f);
+    }
+}
+
+__global__ void k_clip(float2* __restrict__ a, const int64_t n, const float max_norm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 q = a[i];
+    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)));
+    if (d >= max_norm) a[i] = make_float2(__fdiv_rn(q.x, d), __fdiv_rn(q.y, d));
+}
+
+// SwarmEnv.x_update / xv_cutoff / s as standalone element-wise helpers (static methods of the facade)
+__global__ void k_x_update(double2* __restrict__ x, double2* __restrict__ v, const double2* __restrict__ noise,
+                           const int64_t n, const double dt, const int move) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double2 p = x[i], w = v[i];
+    if (p.y <= 0.0) {                      // multiagent.py:77-86, v is mutated like the reference
+        p.y = 0.0; w.x = 0.0;
+        if (w.y <= 0.0) w.y = 0.0;
+    }
+    v[i] = w;
+    if (move) move_particle(p, w, noise[i], dt, 1.0);
+    x[i] = p;
+}
+
+__global__ void k_s_potential(const double* __restrict__ r, double* __restrict__ out, const int64_t n,
+                              const double F, const double L) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __dadd_rn(__dmul_rn(F, exp(-r[i] / L)), -exp(-r[i]));
+}
+
+__global__ void k_philox_draws(const KP kp, const SwarmState st, double2* __restrict__ x0, double2* __restrict__ xa0,
+                               double2* __restrict__ burn, double2* __restrict__ an, double2* __restrict__ pn) {
+    const int e = blockIdx.x;
+    const int N = kp.N, A = kp.A, rows = kp.n_burn + 1;
+    DrawCtx ctx;
+    ctx.key = kp.key;
+    ctx.env = kp.env_off + (uint32_t)e;
+    ctx.episode = st.episode[e];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) x0[(size_t)e * N + i] = draw_uniform2(ctx, STREAM_X0, i);
+    for (int k = threadIdx.x; k < A; k += blockDim.x) xa0[(size_t)e * A + k] = draw_uniform2(ctx, STREAM_XA0, k);
+    for (int r = 0; r < rows; ++r) {
+        for (int k = threadIdx.x; k < A; k += blockDim.x) {
+            if (r < kp.n_burn) burn[((size_t)e * kp.n_burn + r) * A + k] = draw_normal2(ctx, STREAM_BURN, r, k);
+            an[((size_t)e * rows + r) * A + k] = draw_normal2(ctx, STREAM_NOISE_A, r, k);
+        }
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            pn[((size_t)e * rows + r) * N + i] = draw_normal2(ctx, STREAM_NOISE_X, r, i);
+    }
+}
+
+__global__ void k_philox_raw(const uint4* __restrict__ ctr, const uint2* __restrict__ key, uint4* __restrict__ out,
+                             const int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = philox4x32_10(ctr[i], key[i]);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t err, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(err));
+    return SWARM_ERR_LAUNCH;
+}
+
+constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kMaxLocusts = 2048;
+
+int targets_per_thread(int N) { return N <= 128 ? 1 : (N <= 512 ? 2 : 4); }
+
+int block_threads(int N) {
+    const int T = targets_per_thread(N);
+    const int per = (N + T - 1) / T;
+    return ((per + 31) / 32) * 32;
+}
+
+int validate(const SwarmParams* p, int min_agents = 1) {
+    if (!p) return SWARM_ERR_NULL;
+    if (p->n_envs < 1 || p->n_locusts < 1 || p->n_locusts > kMaxLocusts) return SWARM_ERR_SIZE;
+    if (p->n_agents < min_agents || p->n_agents > 255) return SWARM_ERR_SIZE;
+    if (p->grid_size < 2 || p->grid_size > 255) return SWARM_ERR_SIZE;      // positions are uint8
+    if (p->n_burn_in < 0 || p->max_episode_steps < 0) return SWARM_ERR_SIZE;
+    if (p->math_mode != 0 && p->math_mode != 1) return SWARM_ERR_FLAGS;
+    if (smem_bytes(p->n_locusts, p->n_agents, p->grid_size, true) > kMaxSmem) return SWARM_ERR_SIZE;
+    if (p->env_id_offset < 0 || p->env_id_offset + p->n_envs > (int64_t)0xffffffffLL) return SWARM_ERR_SIZE;
+    return SWARM_OK;
+}
+
+KP make_kp(const SwarmParams* p) {
+    KP k;
+    k.E = p->n_envs; k.N = p->n_locusts; k.A = p->n_agents; k.G = p->grid_size;
+    k.n_burn = p->n_burn_in; k.max_steps = p->max_episode_steps;
+    k.sigma = p->noise; k.wind = p->wind; k.dt = p->dt;
+    k.half_w = p->box_width / 2.0; k.y_hi = 2.0 * p->box_height;
+    k.F = (float)p->F;
+    k.negc1 = (float)(-1.4426950408889634);
+    k.negc2 = (float)(-1.4426950408889634 / p->L);
+    k.invL = (float)(1.0 / p->L);
+    k.U = (float)p->wind; k.Gv = (float)p->gravity; k.eps = 1e-6f;
+    k.key = make_uint2((uint32_t)(p->seed & 0xffffffffu), (uint32_t)(p->seed >> 32));
+    k.env_off = (uint32_t)p->env_id_offset;
+    return k;
+}
+
+template <typename K>
+int prep(K kernel, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute");
+    }
+    return SWARM_OK;
+}
+
+int check_launch(const char* what) {
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? SWARM_OK : cuda_fail(err, what);
+}
+
+#define DISPATCH_T(T_, ...)              \
+    switch (T_) {                        \
+        case 1: { constexpr int TT = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int TT = 2; __VA_ARGS__; } break; \
+        default: { constexpr int TT = 4; __VA_ARGS__; } break; \
+    }
+
+const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr};
+
+bool draws_complete(const SwarmInjectedDraws* d) {
+    return d->x0 && d->xa0 && d->burn_actions && d->agent_noise && d->particle_noise;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int swarm_abi_version(void) { return SWARM_ABI_VERSION; }
+
+const char* swarm_strerror(int status) {
+    switch (status) {
+        case SWARM_OK: return "ok";
+        case SWARM_ERR_NULL: return "required pointer is NULL";
+        case SWARM_ERR_SIZE: return "unsupported size (E>=1, 1<=N<=2048, 1<=A<=255, 2<=G<=255, shared memory <= 227 KB)";
+        case SWARM_ERR_LAUNCH: return "CUDA launch/runtime error (see swarm_last_cuda_error)";
+        case SWARM_ERR_FLAGS: return "inconsistent flags or missing optional buffer";
+        default: return "unknown status";
+    }
+}
+
+const char* swarm_last_cuda_error(void) { return g_cuda_err; }
+
+int swarm_validate(const SwarmParams* p) { return validate(p); }
+
+int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask, const SwarmInjectedDraws* draws,
+                swarm_stream_t stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!st || !st->x || !st->xa || !st->noise_x || !st->noise_a || !st->elapsed || !st->episode) return SWARM_ERR_NULL;
+    if (draws && !draws_complete(draws)) return SWARM_ERR_NULL;
+    const KP kp = make_kp(p);
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, false);
+    const int nt = block_threads(kp.N);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(targets_per_thread(kp.N),
+        if (p->math_mode) {
+            if ((rc = prep(k_reset<TT, true>, smem))) return rc;
+            k_reset<TT, true><<<kp.E, nt, smem, s>>>(kp, *st, mask, draws ? *draws : kNoDraws, draws ? 1 : 0);
+        } else {
+            if ((rc = prep(k_reset<TT, false>, smem))) return rc;
+            k_reset<TT, false><<<kp.E, nt, smem, s>>>(kp, *st, mask, draws ? *draws : kNoDraws, draws ? 1 : 0);
+        })
+    return check_launch("swarm_reset");
+}
+
+int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const SwarmInjectedDraws* reset_draws,
+               swarm_stream_t stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!st || !io) return SWARM_ERR_NULL;
+    if (!st->x || !st->xa || !st->noise_x || !st->noise_a || !st->elapsed || !st->episode) return SWARM_ERR_NULL;
+    if (!io->reward || !io->done) return SWARM_ERR_NULL;
+    if ((io->flags & SWARM_STEP_ACTIONS_F64) ? !io->actions_f64 : !io->actions_f32) return SWARM_ERR_NULL;
+    if ((io->grid != nullptr) != (io->positions != nullptr)) return SWARM_ERR_FLAGS;
+    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
+    if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
+    const KP kp = make_kp(p);
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, io->grid != nullptr);
+    const int nt = block_threads(kp.N);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(targets_per_thread(kp.N),
+        if (p->math_mode) {
+            if ((rc = prep(k_step<TT, true>, smem))) return rc;
+            k_step<TT, true><<<kp.E, nt, smem, s>>>(kp, *st, *io, reset_draws ? *reset_draws : kNoDraws, reset_draws ? 1 : 0);
+        } else {
+            if ((rc = prep(k_step<TT, false>, smem))) return rc;
+            k_step<TT, false><<<kp.E, nt, smem, s>>>(kp, *st, *io, reset_draws ? *reset_draws : kNoDraws, reset_draws ? 1 : 0);
+        })
+    return check_launch("swarm_step");
+}
+
+int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const float* host_actions,
+                    float* host_reward, uint8_t* host_done, swarm_stream_t stream) {
+    if (!p || !io || !host_actions || !host_reward || !host_done) return SWARM_ERR_NULL;
+    if ((io->flags & SWARM_STEP_ACTIONS_F64) || !io->actions_f32) return SWARM_ERR_FLAGS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t na = (size_t)p->n_envs * p->n_agents * 2 * sizeof(float);
+    cudaError_t err = cudaMemcpyAsync(io->actions_f32, host_actions, na, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return cuda_fail(err, "H2D actions");
+    const int rc = swarm_step(p, st, io, nullptr, stream);
+    if (rc) return rc;
+    err = cudaMemcpyAsync(host_reward, io->reward, (size_t)p->n_envs * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return cuda_fail(err, "D2H reward");
+    err = cudaMemcpyAsync(host_done, io->done, (size_t)p->n_envs, cudaMemcpyDeviceToHost, s);
+    if (err != cudaSuccess) return cuda_fail(err, "D2H done");
+    err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) return cuda_fail(err, "stream sync");
+    return SWARM_OK;
+}
+
+int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa, float* grid, uint8_t* positions,
+                    double* box, swarm_stream_t stream) {
+    int rc = validate(p, 0);
+    if (rc) return rc;
+    if (!x || !grid) return SWARM_ERR_NULL;
+    if (p->n_agents > 0 && (!xa || !positions)) return SWARM_ERR_NULL;
+    const KP kp = make_kp(p);
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, true);
+    const int nt = block_threads(kp.N);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(targets_per_thread(kp.N),
+        if ((rc = prep(k_rasterize<TT>, smem))) return rc;
+        k_rasterize<TT><<<kp.E, nt, smem, s>>>(kp, x, xa, grid, positions, box);)
+    return check_launch("swarm_rasterize");
+}
+
+int swarm_expand_obs(const SwarmParams* p, const float* grid, const uint8_t* positions, float* expanded,
+                     swarm_stream_t stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!grid || !positions || !expanded) return SWARM_ERR_NULL;
+    const int cells = p->grid_size * p->grid_size;
+    dim3 g((cells + 255) / 256, (unsigned)(p->n_envs * p->n_agents));
+    if (g.y > 65535u) {
+        // split the (e,a) axis over several launches to respect gridDim.y
+        const int per = 65535 / p->n_agents;   // envs per launch
+        for (int e0 = 0; e0 < p->n_envs; e0 += per) {
+            const int ne = (p->n_envs - e0) < per ? (p->n_envs - e0) : per;
+            dim3 gg((cells + 255) / 256, (unsigned)(ne * p->n_agents));
+            k_expand<<<gg, 256, 0, (cudaStream_t)stream>>>(ne, p->n_agents, p->grid_size,
+                reinterpret_cast<const float2*>(grid) + (size_t)e0 * cells, positions + (size_t)e0 * p->n_agents * 2,
+                expanded + (size_t)e0 * p->n_agents * cells * 3);
+        }
+    } else {
+        k_expand<<<g, 256, 0, (cudaStream_t)stream>>>(p->n_envs, p->n_agents, p->grid_size,
+                                                     reinterpret_cast<const float2*>(grid), positions, expanded);
+    }
+    return check_launch("swarm_expand_obs");
+}
+
+int swarm_forces(const SwarmParams* p, const double* x, const double* xa, float* v, float* reward,
+                 swarm_stream_t stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!x || !xa || (!v && !reward)) return SWARM_ERR_NULL;
+    const KP kp = make_kp(p);
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, false);
+    const int nt = block_threads(kp.N);
+    cudaStream_t s = (cudaStream_t)stream;
+    DISPATCH_T(targets_per_thread(kp.N),
+        if (p->math_mode) {
+            if ((rc = prep(k_forces<TT, true>, smem))) return rc;
+            k_forces<TT, true><<<kp.E, nt, smem, s>>>(kp, x, xa, v, reward);
+        } else {
+            if ((rc = prep(k_forces<TT, false>, smem))) return rc;
+            k_forces<TT, false><<<kp.E, nt, smem, s>>>(kp, x, xa, v, reward);
+        })
+    return check_launch("swarm_forces");
+}
+
+int swarm_x_update(double* x, double* v, const double* noise, int64_t n, double dt, swarm_stream_t stream) {
+    if (!x || !v || !noise) return SWARM_ERR_NULL;
+    if (n <= 0) return n == 0 ? SWARM_OK : SWARM_ERR_SIZE;
+    k_x_update<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(v), reinterpret_cast<const double2*>(noise), n, dt, 1);
+    return check_launch("swarm_x_update");
+}
+
+int swarm_xv_cutoff(double* x, double* v, int64_t n, swarm_stream_t stream) {
+    if (!x || !v) return SWARM_ERR_NULL;
+    if (n <= 0) return n == 0 ? SWARM_OK : SWARM_ERR_SIZE;
+    k_x_update<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(v), nullptr, n, 0.0, 0);
+    return check_launch("swarm_xv_cutoff");
+}
+
+int swarm_s_potential(const double* r, double* out, int64_t n, double F, double L, swarm_stream_t stream) {
+    if (!r || !out) return SWARM_ERR_NULL;
+    if (n <= 0) return n == 0 ? SWARM_OK : SWARM_ERR_SIZE;
+    k_s_potential<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(r, out, n, F, L);
+    return check_launch("swarm_s_potential");
+}
+
+int swarm_clip_actions(float* actions, int64_t n_rows, float max_norm, swarm_stream_t stream) {
+    if (!actions) return SWARM_ERR_NULL;
+    if (n_rows < 0) return SWARM_ERR_SIZE;
+    if (n_rows == 0) return SWARM_OK;
+    k_clip<<<(unsigned)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(actions), n_rows,
+                                                                              max_norm);
+    return check_launch("swarm_clip_actions");
+}
+
+int swarm_philox_draws(const SwarmParams* p, const SwarmState* st, double* x0, double* xa0, double* burn_actions,
+                       double* agent_noise, double* particle_noise, swarm_stream_t stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (!st || !st->episode || !x0 || !xa0 || !burn_actions || !agent_noise || !particle_noise) return SWARM_ERR_NULL;
+    const KP kp = make_kp(p);
+    k_philox_draws<<<kp.E, 128, 0, (cudaStream_t)stream>>>(kp, *st, reinterpret_cast<double2*>(x0),
+        reinterpret_cast<double2*>(xa0), reinterpret_cast<double2*>(burn_actions),
+        reinterpret_cast<double2*>(agent_noise), reinterpret_cast<double2*>(particle_noise));
+    return check_launch("swarm_philox_draws");
+}
+
+int swarm_philox_raw(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int64_t n, swarm_stream_t stream) {
+    if (!ctr || !key || !out) return SWARM_ERR_NULL;
+    if (n <= 0) return n == 0 ? SWARM_OK : SWARM_ERR_SIZE;
+    k_philox_raw<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(ctr), reinterpret_cast<const uint2*>(key), reinterpret_cast<uint4*>(out), n);
+    return check_launch("swarm_philox_raw");
+}
+
+}  // extern "C"

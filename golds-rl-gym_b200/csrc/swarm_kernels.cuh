@@ -1,0 +1,365 @@
+// Block-level device code of the swarm hot path (sm_100a).  One CTA owns one env:
+//   * the env's FP64 integrator state lives in shared memory for the whole kernel
+//     (step, auto-reset burn-in and rasterise never round-trip through HBM),
+//   * the O(N^2) pair forces run in FP32 on a swarm-centred FP32 copy of the positions
+//     staged in shared memory (broadcast LDS.128 = two sources per load, T targets per
+//     thread in registers),
+//   * reward is a warp-shuffle + shared-memory reduction in FP64,
+//   * the occupancy grid is a shared-memory-privatised histogram with warp-aggregated
+//     atomics (match.any), written out as a streaming zero fill + sparse scatter.
+//
+// Reference semantics restated here: fed_gym/envs/multiagent.py:30-115,
+// fed_gym/agents/state_processors.py:25-42.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swarm_b200.h"
+#include "swarm_philox.cuh"
+
+namespace swarm {
+
+// Kernel-side parameter block (derived from SwarmParams on the host).
+struct KP {
+    int E, N, A, G, n_burn, max_steps;
+    double sigma, wind, dt, half_w, y_hi;
+    float F, negc1, negc2, invL, U, Gv, eps;
+    uint2 key;
+    uint32_t env_off;
+};
+
+struct Smem {
+    double2* xs;      // N   locust positions (FP64 integrator state)
+    double2* as;      // A   agent positions
+    double2* act;     // A   current actions
+    double2* an;      // A   current agent noise row (unscaled)
+    float2* src;      // N+A FP32 sources relative to the swarm centre (16B aligned)
+    double* red;      // 32  reduction scratch
+    double* box;      // 2   rasteriser: mean x
+    uint32_t* table;  // G*G packed cell counters: lo16 locusts, hi16 agents
+};
+
+__host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
+
+__host__ __device__ inline size_t smem_bytes(int N, int A, int G, bool raster) {
+    size_t b = 0;
+    b += smem_align(sizeof(double2) * N);
+    b += 3 * smem_align(sizeof(double2) * A);
+    b += smem_align(sizeof(float2) * (N + A + 2));
+    b += smem_align(sizeof(double) * 32);
+    b += smem_align(sizeof(double) * 2);
+    if (raster) b += smem_align(sizeof(uint32_t) * G * G);
+    return b;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, bool raster) {
+    Smem s;
+    size_t o = 0;
+    s.xs = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * N);
+    s.as = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
+    s.act = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * A);
+    s.an = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
+    s.src = reinterpret_cast<float2*>(base + o);  o += smem_align(sizeof(float2) * (N + A + 2));
+    s.red = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 32);
+    s.box = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 2);
+    s.table = raster ? reinterpret_cast<uint32_t*>(base + o) : nullptr;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// multiagent.py:70-86  x_update = cutoff; x += dt*v + noise; cutoff   (FP64, no FMA contraction
+// so that an injected v reproduces the reference's three roundings exactly)
+__device__ __forceinline__ void move_particle(double2& p, double2 v, double2 n, double dt, double sigma) {
+    if (p.y <= 0.0) {
+        p.y = 0.0;
+        v.x = 0.0;
+        if (v.y <= 0.0) v.y = 0.0;
+    }
+    p.x = __dadd_rn(p.x, __dadd_rn(__dmul_rn(dt, v.x), __dmul_rn(sigma, n.x)));
+    p.y = __dadd_rn(p.y, __dadd_rn(__dmul_rn(dt, v.y), __dmul_rn(sigma, n.y)));
+    if (p.y <= 0.0) p.y = 0.0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// One ordered pair (source i -> target j), multiagent.py:65-68,100-113:
+//   w = s(r)/(r+eps), s(r) = F exp(-r/L) - exp(-r);  acc += w * (x_i - x_j)
+// The self pair (and any coincident pair) has dx=dy=0 and contributes exactly 0.
+template <bool PRECISE>
+__device__ __forceinline__ void pair_force(float sx, float sy, float tx, float ty, const KP& kp,
+                                           float& ax, float& ay) {
+    const float dx = sx - tx;
+    const float dy = sy - ty;
+    if (PRECISE) {
+        const float r = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        const float s = __fmaf_rn(kp.F, expf(-r * kp.invL), -expf(-r));
+        const float w = __fdiv_rn(s, __fadd_rn(r, kp.eps));
+        ax = __fmaf_rn(w, dx, ax);
+        ay = __fmaf_rn(w, dy, ay);
+    } else {
+        // r2 >= 1e-30 keeps rsqrt finite for coincident points (their dx,dy are 0 anyway)
+        const float r2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));
+        float rinv, e1, e2, inv;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
+        const float r = r2 * rinv;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(r * kp.negc1));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(r * kp.negc2));
+        const float s = fmaf(kp.F, e2, -e1);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + kp.eps));
+        const float w = s * inv;
+        ax = fmaf(w, dx, ax);
+        ay = fmaf(w, dy, ay);
+    }
+}
+
+// Stage the FP32 sources: locusts then agents, x relative to a swarm centre (mean x of the
+// first <=32 locusts, identical in every warp) so FP32 keeps ~1e-7 absolute resolution while
+// the wind carries the swarm to x ~ 8.
+__device__ __forceinline__ void stage_sources(const Smem& sm, int N, int A) {
+    const int lane = threadIdx.x & 31;
+    const int nc = N < 32 ? N : 32;
+    const double cx = warp_sum(lane < nc ? sm.xs[lane].x : 0.0) / (double)nc;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double2 p = sm.xs[i];
+        sm.src[i] = make_float2((float)(p.x - cx), (float)p.y);
+    }
+    for (int k = threadIdx.x; k < A; k += blockDim.x) {
+        const double2 p = sm.as[k];
+        sm.src[N + k] = make_float2((float)(p.x - cx), (float)p.y);
+    }
+}
+
+// All-pairs forces for this thread's T targets (j = tid + t*blockDim.x); returns pre-cutoff v
+// (wind and gravity added) and the block-wide reward = -mean_j |v_j|^2.
+template <int T, bool PRECISE>
+__device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, float (&vx)[T], float (&vy)[T]) {
+    const int N = kp.N, S = kp.N + kp.A;
+    float tx[T], ty[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int j = threadIdx.x + t * blockDim.x;
+        const float2 q = sm.src[j < N ? j : N - 1];
+        tx[t] = q.x; ty[t] = q.y;
+        vx[t] = 0.f; vy[t] = 0.f;
+    }
+    const float4* s4 = reinterpret_cast<const float4*>(sm.src);
+    const int S2 = S >> 1;
+#pragma unroll 2
+    for (int i = 0; i < S2; ++i) {
+        const float4 q = s4[i];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            pair_force<PRECISE>(q.x, q.y, tx[t], ty[t], kp, vx[t], vy[t]);
+            pair_force<PRECISE>(q.z, q.w, tx[t], ty[t], kp, vx[t], vy[t]);
+        }
+    }
+    if (S & 1) {
+        const float2 q = sm.src[S - 1];
+#pragma unroll
+        for (int t = 0; t < T; ++t) pair_force<PRECISE>(q.x, q.y, tx[t], ty[t], kp, vx[t], vy[t]);
+    }
+    double e = 0.0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        vx[t] += kp.U;
+        vy[t] += kp.Gv;
+        if (threadIdx.x + t * blockDim.x < N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
+    }
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    double tot = 0.0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) tot += sm.red[w];   // same order in every thread
+    return -tot / (double)N;
+}
+
+// SwarmEnv._step on the shared-memory state.  Preconditions: sm.xs/as/act/an filled and
+// visible (a __syncthreads since their last write); nx[t] = unscaled noise of own target t.
+// Postcondition: state updated and visible to the whole block.
+template <int T, bool PRECISE>
+__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const double2 (&nx)[T], float* v_out) {
+    // multiagent.py:33-38  agents move first: v_action (+wind on x) through x_update
+    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) {
+        double2 a = sm.as[k];
+        double2 w = sm.act[k];
+        w.x = __dadd_rn(w.x, kp.wind);
+        move_particle(a, w, sm.an[k], kp.dt, kp.sigma);
+        sm.as[k] = a;
+    }
+    __syncthreads();
+    stage_sources(sm, kp.N, kp.A);       // old x, NEW xa (multiagent.py:39)
+    __syncthreads();
+    float vx[T], vy[T];
+    const double reward = pair_forces<T, PRECISE>(sm, kp, vx, vy);
+    // multiagent.py:40  locusts move with the pre-cutoff v just computed
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int j = threadIdx.x + t * blockDim.x;
+        if (j < kp.N) {
+            if (v_out) reinterpret_cast<float2*>(v_out)[j] = make_float2(vx[t], vy[t]);
+            double2 p = sm.xs[j];
+            move_particle(p, make_double2((double)vx[t], (double)vy[t]), nx[t], kp.dt, kp.sigma);
+            sm.xs[j] = p;
+        }
+    }
+    __syncthreads();
+    return reward;
+}
+
+// SwarmEnv._reset (multiagent.py:46-63) for env e: draws (injected or Philox), n_burn burn-in
+// steps with noise row k, then the frozen row n_burn is stored for all later steps (Q1).
+template <int T, bool PRECISE>
+__device__ __forceinline__ void env_reset(const Smem& sm, const KP& kp, int e, uint32_t episode,
+                                          const bool inj, const SwarmInjectedDraws& dr, const SwarmState& st) {
+    const int N = kp.N, A = kp.A;
+    DrawCtx ctx;
+    ctx.key = kp.key;
+    ctx.env = kp.env_off + (uint32_t)e;
+    ctx.episode = episode;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        sm.xs[i] = inj ? reinterpret_cast<const double2*>(dr.x0)[(size_t)e * N + i]
+                       : draw_uniform2(ctx, STREAM_X0, i);
+    for (int k = threadIdx.x; k < A; k += blockDim.x)
+        sm.as[k] = inj ? reinterpret_cast<const double2*>(dr.xa0)[(size_t)e * A + k]
+                       : draw_uniform2(ctx, STREAM_XA0, k);
+    const int rows = kp.n_burn + 1;
+    for (int r = 0; r <= kp.n_burn; ++r) {
+        double2 nx[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = threadIdx.x + t * blockDim.x;
+            nx[t] = make_double2(0.0, 0.0);
+            if (j < N)
+                nx[t] = inj ? reinterpret_cast<const double2*>(dr.particle_noise)[((size_t)e * rows + r) * N + j]
+                            : draw_normal2(ctx, STREAM_NOISE_X, r, j);
+        }
+        if (r == kp.n_burn) {   // frozen row: kept in HBM for every later step
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int j = threadIdx.x + t * blockDim.x;
+                if (j < N) reinterpret_cast<double2*>(st.noise_x)[(size_t)e * N + j] = nx[t];
+            }
+            for (int k = threadIdx.x; k < A; k += blockDim.x)
+                reinterpret_cast<double2*>(st.noise_a)[(size_t)e * A + k] =
+                    inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
+                        : draw_normal2(ctx, STREAM_NOISE_A, r, k);
+            break;
+        }
+        for (int k = threadIdx.x; k < A; k += blockDim.x) {
+            sm.act[k] = inj ? reinterpret_cast<const double2*>(dr.burn_actions)[((size_t)e * kp.n_burn + r) * A + k]
+                            : draw_normal2(ctx, STREAM_BURN, r, k);
+            sm.an[k] = inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
+                           : draw_normal2(ctx, STREAM_NOISE_A, r, k);
+        }
+        __syncthreads();
+        env_step<T, PRECISE>(sm, kp, nx, nullptr);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// np.searchsorted(edges, p, side='right') for edges = linspace(lo, hi, G+1) as numpy builds
+// them: e[i] = fl(fl(i*step) + lo) for i < G, e[G] = hi  (numpy/_core/function_base.py).
+__device__ __forceinline__ double edge_at(int i, double lo, double hi, double step, int G) {
+    return i >= G ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
+}
+
+__device__ __forceinline__ int count_le(double p, double lo, double hi, double step, int G) {
+    if (!(p == p)) return G + 1;                 // NaN sorts last
+    const double q = (p - lo) / step;
+    int g = q < -1.0 ? -1 : (q > (double)G ? G : (int)floor(q));
+    while (g < G && edge_at(g + 1, lo, hi, step, G) <= p) ++g;
+    while (g >= 0 && edge_at(g, lo, hi, step, G) > p) --g;
+    return g + 1;                                // #{i in [0,G] : e[i] <= p}
+}
+
+// SwarmStateProcessor.process_state (state_processors.py:25-42) of the shared-memory state.
+// MAXIT >= ceil((N+A)/blockDim.x).  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
+template <int MAXIT>
+__device__ __forceinline__ void env_raster(const Smem& sm, const KP& kp, float* __restrict__ grid_e,
+                                           uint8_t* __restrict__ pos_e) {
+    const int N = kp.N, A = kp.A, G = kp.G, P = N + A, cells = G * G;
+    // phase 0: one thread walks the sequential FP64 mean (np.mean(vstack([x,xa]),axis=0)[0] is a
+    // plain left-to-right sum); everyone else clears the counters and streams zeros to HBM.
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < N; ++i) s = __dadd_rn(s, sm.xs[i].x);
+        for (int k = 0; k < A; ++k) s = __dadd_rn(s, sm.as[k].x);
+        sm.box[0] = s / (double)P;
+    }
+    {
+        const int first = blockDim.x > 32 ? 32 : 0;     // warp 0 is busy with the mean
+        const int nt = blockDim.x - first;
+        const int t = (int)threadIdx.x - first;
+        if (t >= 0) {
+            if ((cells & 1) == 0) {
+                float4* g4 = reinterpret_cast<float4*>(grid_e);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = t; i < cells / 2; i += nt) __stcs(g4 + i, z);
+            } else {
+                float2* g2 = reinterpret_cast<float2*>(grid_e);
+                for (int i = t; i < cells; i += nt) __stcs(g2 + i, make_float2(0.f, 0.f));
+            }
+        }
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.table[i] = 0u;
+    }
+    __syncthreads();
+    // phase 1: bin every point in FP64 against numpy's edges, count with warp-aggregated atomics
+    const double m = sm.box[0];
+    const double lo_x = m - kp.half_w, hi_x = m + kp.half_w;
+    const double step_x = (hi_x - lo_x) / (double)G;
+    const double lo_y = 0.0, hi_y = kp.y_hi;
+    const double step_y = (hi_y - lo_y) / (double)G;
+    int wcell[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) wcell[it] = -1;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int base = it * blockDim.x;
+        if (base >= P) break;
+        const int p = base + threadIdx.x;
+        uint32_t key = 0xffffffffu;
+        int cell = 0;
+        if (p < P) {
+            const bool agent = p >= N;
+            const double2 q = agent ? sm.as[p - N] : sm.xs[p];
+            const int cx = count_le(q.x, lo_x, hi_x, step_x, G);
+            const int cy = count_le(q.y, lo_y, hi_y, step_y, G);
+            if (agent) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
+                pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
+                pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
+            }
+            const int bx = (q.x == hi_x) ? cx - 2 : cx - 1;   // histogramdd right-edge fix-up
+            const int by = (q.y == hi_y) ? cy - 2 : cy - 1;
+            if (bx >= 0 && bx < G && by >= 0 && by < G) {
+                cell = bx * G + by;
+                key = ((uint32_t)cell << 1) | (agent ? 1u : 0u);
+            }
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (key != 0xffffffffu && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+            const uint32_t inc = (uint32_t)__popc(peers) << ((key & 1u) ? 16 : 0);
+            const uint32_t old = atomicAdd(&sm.table[cell], inc);
+            if (old == 0u) wcell[it] = cell;          // first arrival writes the cell out
+        }
+    }
+    __syncthreads();
+    // phase 2: sparse scatter of the non-zero cells over the zero fill
+    float2* g2 = reinterpret_cast<float2*>(grid_e);
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        if (wcell[it] >= 0) {
+            const uint32_t w = sm.table[wcell[it]];
+            g2[wcell[it]] = make_float2(__fdiv_rn((float)(w & 0xffffu), (float)N),
+                                        A > 0 ? __fdiv_rn((float)(w >> 16), (float)A) : 0.f);
+        }
+    }
+}
+
+}  // namespace swarm

@@ -88,7 +88,7 @@ def load_reference_runner():
         sys.modules["fed_gym.agents.paac"].__path__ = [os.path.join(REFERENCE_ROOT, "fed_gym", "agents", "paac")]
         sys.modules["fed_gym.agents.a3c"].__path__ = []
         sys.modules["fed_gym.agents.a3c.worker"].sigmoid = lambda x: x
-        sys.modules["fed_gym.agents.state_processors"].SwarmStateProcessor = sp.SwarmStateProcessor
+        sys.modules["fed_gym.agents.state_processors"] = sp     # the real module, loaded by path
         mod = importlib.import_module("fed_gym.agents.paac.emulator_runner")
         runner = mod.SwarmRunner
     finally:
