@@ -1,9 +1,9 @@
 // Block-level device code of the swarm hot path (sm_100a).  One CTA owns one env:
 //   * the env's FP64 integrator state lives in shared memory for the whole kernel
 //     (step, auto-reset burn-in and rasterise never round-trip through HBM),
-//   * the O(N^2) pair forces run in FP32 on a swarm-centred FP32 copy of the positions
-//     staged in shared memory (broadcast LDS.128 = two sources per load, T targets per
-//     thread in registers),
+//   * the O(N^2) pair forces run in FP32 on an FP32 hi/lo split of the positions staged in
+//     shared memory (broadcast LDS.128 = one source per load, T targets per thread in
+//     registers),
 //   * reward is a warp-shuffle + shared-memory reduction in FP64,
 //   * the occupancy grid is a shared-memory-privatised histogram with warp-aggregated
 //     atomics (match.any), written out as a streaming zero fill + sparse scatter.
@@ -33,7 +33,7 @@ struct Smem {
     double2* as;      // A   agent positions
     double2* act;     // A   current actions
     double2* an;      // A   current agent noise row (unscaled)
-    float2* src;      // N+A FP32 sources relative to the swarm centre (16B aligned)
+    float4* src;      // N+A FP32 sources as (hi_x, hi_y, lo_x, lo_y): x = hi + lo to ~2^-48
     double* red;      // 32  reduction scratch
     double* box;      // 2   rasteriser: mean x
     uint32_t* table;  // G*G packed cell counters: lo16 locusts, hi16 agents
@@ -45,7 +45,7 @@ __host__ __device__ inline size_t smem_bytes(int N, int A, int G, bool raster) {
     size_t b = 0;
     b += smem_align(sizeof(double2) * N);
     b += 3 * smem_align(sizeof(double2) * A);
-    b += smem_align(sizeof(float2) * (N + A + 2));
+    b += smem_align(sizeof(float4) * (N + A));
     b += smem_align(sizeof(double) * 32);
     b += smem_align(sizeof(double) * 2);
     if (raster) b += smem_align(sizeof(uint32_t) * G * G);
@@ -59,7 +59,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     s.as = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
     s.act = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * A);
     s.an = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
-    s.src = reinterpret_cast<float2*>(base + o);  o += smem_align(sizeof(float2) * (N + A + 2));
+    s.src = reinterpret_cast<float4*>(base + o);  o += smem_align(sizeof(float4) * (N + A));
     s.red = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 32);
     s.box = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 2);
     s.table = raster ? reinterpret_cast<uint32_t*>(base + o) : nullptr;
@@ -89,12 +89,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------------------------------
 // One ordered pair (source i -> target j), multiagent.py:65-68,100-113:
 //   w = s(r)/(r+eps), s(r) = F exp(-r/L) - exp(-r);  acc += w * (x_i - x_j)
-// The self pair (and any coincident pair) has dx=dy=0 and contributes exactly 0.
+// Positions arrive as FP32 hi/lo pairs of the FP64 state, so the difference
+//   d = (hi_i - hi_j) + (lo_i - lo_j)
+// carries ~2^-24 RELATIVE error however close the two particles are (plain FP32 positions lose
+// the direction of close pairs, where s/(r+eps) is steepest).  The self pair (and any coincident
+// pair) has d = 0 exactly and contributes exactly 0.
 template <bool PRECISE>
-__device__ __forceinline__ void pair_force(float sx, float sy, float tx, float ty, const KP& kp,
-                                           float& ax, float& ay) {
-    const float dx = sx - tx;
-    const float dy = sy - ty;
+__device__ __forceinline__ void pair_force(const float4 q, const float4 tg, const KP& kp, float& ax, float& ay) {
+    const float dx = (q.x - tg.x) + (q.z - tg.z);
+    const float dy = (q.y - tg.y) + (q.w - tg.w);
     if (PRECISE) {
         const float r = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
         const float s = __fmaf_rn(kp.F, expf(-r * kp.invL), -expf(-r));
@@ -117,21 +120,15 @@ __device__ __forceinline__ void pair_force(float sx, float sy, float tx, float t
     }
 }
 
-// Stage the FP32 sources: locusts then agents, x relative to a swarm centre (mean x of the
-// first <=32 locusts, identical in every warp) so FP32 keeps ~1e-7 absolute resolution while
-// the wind carries the swarm to x ~ 8.
+__device__ __forceinline__ float4 split_hilo(const double2 p) {
+    const float hx = (float)p.x, hy = (float)p.y;
+    return make_float4(hx, hy, (float)(p.x - (double)hx), (float)(p.y - (double)hy));
+}
+
+// Stage the FP32 hi/lo sources: locusts then agents.
 __device__ __forceinline__ void stage_sources(const Smem& sm, int N, int A) {
-    const int lane = threadIdx.x & 31;
-    const int nc = N < 32 ? N : 32;
-    const double cx = warp_sum(lane < nc ? sm.xs[lane].x : 0.0) / (double)nc;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const double2 p = sm.xs[i];
-        sm.src[i] = make_float2((float)(p.x - cx), (float)p.y);
-    }
-    for (int k = threadIdx.x; k < A; k += blockDim.x) {
-        const double2 p = sm.as[k];
-        sm.src[N + k] = make_float2((float)(p.x - cx), (float)p.y);
-    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.src[i] = split_hilo(sm.xs[i]);
+    for (int k = threadIdx.x; k < A; k += blockDim.x) sm.src[N + k] = split_hilo(sm.as[k]);
 }
 
 // All-pairs forces for this thread's T targets (j = tid + t*blockDim.x); returns pre-cutoff v
@@ -139,29 +136,18 @@ __device__ __forceinline__ void stage_sources(const Smem& sm, int N, int A) {
 template <int T, bool PRECISE>
 __device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, float (&vx)[T], float (&vy)[T]) {
     const int N = kp.N, S = kp.N + kp.A;
-    float tx[T], ty[T];
+    float4 tg[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int j = threadIdx.x + t * blockDim.x;
-        const float2 q = sm.src[j < N ? j : N - 1];
-        tx[t] = q.x; ty[t] = q.y;
+        tg[t] = sm.src[j < N ? j : N - 1];
         vx[t] = 0.f; vy[t] = 0.f;
     }
-    const float4* s4 = reinterpret_cast<const float4*>(sm.src);
-    const int S2 = S >> 1;
-#pragma unroll 2
-    for (int i = 0; i < S2; ++i) {
-        const float4 q = s4[i];
+#pragma unroll 4
+    for (int i = 0; i < S; ++i) {
+        const float4 q = sm.src[i];              // broadcast LDS.128: one source for the whole warp
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            pair_force<PRECISE>(q.x, q.y, tx[t], ty[t], kp, vx[t], vy[t]);
-            pair_force<PRECISE>(q.z, q.w, tx[t], ty[t], kp, vx[t], vy[t]);
-        }
-    }
-    if (S & 1) {
-        const float2 q = sm.src[S - 1];
-#pragma unroll
-        for (int t = 0; t < T; ++t) pair_force<PRECISE>(q.x, q.y, tx[t], ty[t], kp, vx[t], vy[t]);
+        for (int t = 0; t < T; ++t) pair_force<PRECISE>(q, tg[t], kp, vx[t], vy[t]);
     }
     double e = 0.0;
 #pragma unroll

@@ -314,7 +314,7 @@ class SwarmEnv(object):
         lib = nat.load()
         x_t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).cuda()
         v_t = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64)).cuda()
-        n_t = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(noise, x.shape), dtype=np.float64)).cuda()
+        n_t = torch.as_tensor(np.array(np.broadcast_to(noise, x.shape), dtype=np.float64)).cuda()
         nat.check(lib.swarm_x_update(_ptr(x_t), _ptr(v_t), _ptr(n_t), x_t.shape[0], float(dt),
                                      _stream(x_t.device)), "swarm_x_update")
         x[...] = x_t.cpu().numpy()
