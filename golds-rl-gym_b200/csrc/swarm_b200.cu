@@ -14,14 +14,15 @@ namespace {
 // ------------------------------------------------------------------------------------------ kernels
 
 // SwarmEnv._step + TimeLimit + SwarmRunner auto-reset + process_state, one CTA per env.
-template <int T, bool PRECISE>
-__global__ void __launch_bounds__(512) k_step(const KP kp, const SwarmState st, const SwarmStepIO io,
+template <int MODE, bool PRECISE>
+__global__ void __launch_bounds__(512, 2) k_step(const KP kp, const SwarmState st, const SwarmStepIO io,
                                               const SwarmInjectedDraws dr, const int has_draws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     const int N = kp.N, A = kp.A;
+    constexpr int T = ModeT<MODE>::T;
     const bool raster = io.grid != nullptr;
-    const Smem sm = carve(smem_raw, N, A, kp.G, raster);
+    const Smem sm = carve(smem_raw, N, A, MODE == 1);
 
     // state -> shared memory: one double2 (LDG.128) per particle, fully coalesced
     const double2* gx = reinterpret_cast<const double2*>(st.x) + (size_t)e * N;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(512) k_step(const KP kp, const SwarmState st, 
     }
     __syncthreads();
 
-    const double reward = env_step<T, PRECISE>(sm, kp, nx, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
+    const double reward = env_step<MODE, PRECISE>(sm, kp, nx, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
 
     // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
     int elapsed = st.elapsed[e] + 1;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(512) k_step(const KP kp, const SwarmState st, 
         // emulator_runner.py:127-132: the terminal reward/done are reported, the state (and
         // therefore the observation) is the freshly reset episode's.  Block-uniform branch.
         const uint32_t ep = st.episode[e];
-        env_reset<T, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
+        env_reset<MODE, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
         elapsed = 0;
         if (threadIdx.x == 0) st.episode[e] = ep + 1;
     }
@@ -98,15 +99,15 @@ __global__ void __launch_bounds__(512) k_step(const KP kp, const SwarmState st, 
 }
 
 // SwarmEnv._reset for the masked envs.
-template <int T, bool PRECISE>
-__global__ void __launch_bounds__(512) k_reset(const KP kp, const SwarmState st, const uint8_t* __restrict__ mask,
+template <int MODE, bool PRECISE>
+__global__ void __launch_bounds__(512, 2) k_reset(const KP kp, const SwarmState st, const uint8_t* __restrict__ mask,
                                                const SwarmInjectedDraws dr, const int has_draws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, false);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, MODE == 1);
     const uint32_t ep = st.episode[e];
-    env_reset<T, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
+    env_reset<MODE, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
     double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * kp.N;
     double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * kp.A;
     for (int i = threadIdx.x; i < kp.N; i += blockDim.x) ox[i] = sm.xs[i];
@@ -118,13 +119,14 @@ __global__ void __launch_bounds__(512) k_reset(const KP kp, const SwarmState st,
 }
 
 // SwarmStateProcessor.process_state for the batch.
-template <int T>
-__global__ void __launch_bounds__(512) k_rasterize(const KP kp, const double* __restrict__ x,
+template <int MODE>
+__global__ void __launch_bounds__(512, 2) k_rasterize(const KP kp, const double* __restrict__ x,
                                                    const double* __restrict__ xa, float* __restrict__ grid,
                                                    uint8_t* __restrict__ positions, double* __restrict__ box) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, true);
+    constexpr int T = ModeT<MODE>::T;
+    const Smem sm = carve(smem_raw, kp.N, kp.A, MODE == 1);
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
     for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
@@ -141,22 +143,23 @@ __global__ void __launch_bounds__(512) k_rasterize(const KP kp, const double* __
 }
 
 // SwarmEnv.v_calculate for the batch (no integration).
-template <int T, bool PRECISE>
-__global__ void __launch_bounds__(512) k_forces(const KP kp, const double* __restrict__ x,
+template <int MODE, bool PRECISE>
+__global__ void __launch_bounds__(512, 2) k_forces(const KP kp, const double* __restrict__ x,
                                                 const double* __restrict__ xa, float* __restrict__ v,
                                                 float* __restrict__ reward) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, false);
+    constexpr int T = ModeT<MODE>::T;
+    const Smem sm = carve(smem_raw, kp.N, kp.A, MODE == 1);
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
     for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
     for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
     __syncthreads();
-    stage_sources(sm, kp.N, kp.A);
+    stage_sources<MODE>(sm, kp);
     __syncthreads();
     float vx[T], vy[T];
-    const double r = pair_forces<T, PRECISE>(sm, kp, vx, vy);
+    const double r = pair_forces<MODE, PRECISE>(sm, kp, vx, vy);
     if (v) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -252,10 +255,11 @@ int cuda_fail(cudaError_t err, const char* what) {
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kMaxLocusts = 2048;
 
-int targets_per_thread(int N) { return N <= 128 ? 1 : (N <= 512 ? 2 : 4); }
+// MODE 1: unordered pairs, one thread per locust (N <= 512); MODE 2/4: ordered pairs, T targets per thread
+int force_mode(int N) { return N <= kSymMaxLocusts ? 1 : (N <= 1024 ? 2 : 4); }
 
 int block_threads(int N) {
-    const int T = targets_per_thread(N);
+    const int T = force_mode(N);
     const int per = (N + T - 1) / T;
     return ((per + 31) / 32) * 32;
 }
@@ -263,11 +267,11 @@ int block_threads(int N) {
 int validate(const SwarmParams* p, int min_agents = 1) {
     if (!p) return SWARM_ERR_NULL;
     if (p->n_envs < 1 || p->n_locusts < 1 || p->n_locusts > kMaxLocusts) return SWARM_ERR_SIZE;
-    if (p->n_agents < min_agents || p->n_agents > 255) return SWARM_ERR_SIZE;
+    if (p->n_agents < min_agents || p->n_agents > 32) return SWARM_ERR_SIZE;
     if (p->grid_size < 2 || p->grid_size > 255) return SWARM_ERR_SIZE;      // positions are uint8
     if (p->n_burn_in < 0 || p->max_episode_steps < 0) return SWARM_ERR_SIZE;
     if (p->math_mode != 0 && p->math_mode != 1) return SWARM_ERR_FLAGS;
-    if (smem_bytes(p->n_locusts, p->n_agents, p->grid_size, true) > kMaxSmem) return SWARM_ERR_SIZE;
+    if (smem_bytes(p->n_locusts, p->n_agents, p->grid_size, true, force_mode(p->n_locusts) == 1) > kMaxSmem) return SWARM_ERR_SIZE;
     if (p->env_id_offset < 0 || p->env_id_offset + p->n_envs > (int64_t)0xffffffffLL) return SWARM_ERR_SIZE;
     return SWARM_OK;
 }
@@ -278,11 +282,11 @@ KP make_kp(const SwarmParams* p) {
     k.n_burn = p->n_burn_in; k.max_steps = p->max_episode_steps;
     k.sigma = p->noise; k.wind = p->wind; k.dt = p->dt;
     k.half_w = p->box_width / 2.0; k.y_hi = 2.0 * p->box_height;
+    k.cscale = 1.4426950408889634;                 // log2(e): exp(-r) == exp2(-c r)
     k.F = (float)p->F;
-    k.negc1 = (float)(-1.4426950408889634);
-    k.negc2 = (float)(-1.4426950408889634 / p->L);
-    k.invL = (float)(1.0 / p->L);
-    k.U = (float)p->wind; k.Gv = (float)p->gravity; k.eps = 1e-6f;
+    k.nInvL = (float)(-1.0 / p->L);
+    k.U = (float)p->wind; k.Gv = (float)p->gravity;
+    k.eps_s = (float)(1e-6 * 1.4426950408889634);  // multiagent.py:103 "+ 0.000001", scaled
     k.key = make_uint2((uint32_t)(p->seed & 0xffffffffu), (uint32_t)(p->seed >> 32));
     k.env_off = (uint32_t)p->env_id_offset;
     return k;
@@ -308,6 +312,7 @@ int check_launch(const char* what) {
         case 2: { constexpr int TT = 2; __VA_ARGS__; } break; \
         default: { constexpr int TT = 4; __VA_ARGS__; } break; \
     }
+#define SMEM(kp_, raster_) smem_bytes((kp_).N, (kp_).A, (kp_).G, (raster_), force_mode((kp_).N) == 1)
 
 const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -327,7 +332,7 @@ const char* swarm_strerror(int status) {
     switch (status) {
         case SWARM_OK: return "ok";
         case SWARM_ERR_NULL: return "required pointer is NULL";
-        case SWARM_ERR_SIZE: return "unsupported size (E>=1, 1<=N<=2048, 1<=A<=255, 2<=G<=255, shared memory <= 227 KB)";
+        case SWARM_ERR_SIZE: return "unsupported size (E>=1, 1<=N<=2048, 1<=A<=32, 2<=G<=255, shared memory <= 227 KB)";
         case SWARM_ERR_LAUNCH: return "CUDA launch/runtime error (see swarm_last_cuda_error)";
         case SWARM_ERR_FLAGS: return "inconsistent flags or missing optional buffer";
         default: return "unknown status";
@@ -345,10 +350,10 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
     if (!st || !st->x || !st->xa || !st->noise_x || !st->noise_a || !st->elapsed || !st->episode) return SWARM_ERR_NULL;
     if (draws && !draws_complete(draws)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, false);
+    const size_t smem = SMEM(kp, false);
     const int nt = block_threads(kp.N);
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(targets_per_thread(kp.N),
+    DISPATCH_T(force_mode(kp.N),
         if (p->math_mode) {
             if ((rc = prep(k_reset<TT, true>, smem))) return rc;
             k_reset<TT, true><<<kp.E, nt, smem, s>>>(kp, *st, mask, draws ? *draws : kNoDraws, draws ? 1 : 0);
@@ -371,10 +376,10 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
     if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, io->grid != nullptr);
+    const size_t smem = SMEM(kp, io->grid != nullptr);
     const int nt = block_threads(kp.N);
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(targets_per_thread(kp.N),
+    DISPATCH_T(force_mode(kp.N),
         if (p->math_mode) {
             if ((rc = prep(k_step<TT, true>, smem))) return rc;
             k_step<TT, true><<<kp.E, nt, smem, s>>>(kp, *st, *io, reset_draws ? *reset_draws : kNoDraws, reset_draws ? 1 : 0);
@@ -411,10 +416,10 @@ int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa, flo
     if (!x || !grid) return SWARM_ERR_NULL;
     if (p->n_agents > 0 && (!xa || !positions)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, true);
+    const size_t smem = SMEM(kp, true);
     const int nt = block_threads(kp.N);
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(targets_per_thread(kp.N),
+    DISPATCH_T(force_mode(kp.N),
         if ((rc = prep(k_rasterize<TT>, smem))) return rc;
         k_rasterize<TT><<<kp.E, nt, smem, s>>>(kp, x, xa, grid, positions, box);)
     return check_launch("swarm_rasterize");
@@ -450,10 +455,10 @@ int swarm_forces(const SwarmParams* p, const double* x, const double* xa, float*
     if (rc) return rc;
     if (!x || !xa || (!v && !reward)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, false);
+    const size_t smem = SMEM(kp, false);
     const int nt = block_threads(kp.N);
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(targets_per_thread(kp.N),
+    DISPATCH_T(force_mode(kp.N),
         if (p->math_mode) {
             if ((rc = prep(k_forces<TT, true>, smem))) return rc;
             k_forces<TT, true><<<kp.E, nt, smem, s>>>(kp, x, xa, v, reward);

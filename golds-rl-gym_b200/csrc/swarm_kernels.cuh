@@ -1,12 +1,17 @@
 // Block-level device code of the swarm hot path (sm_100a).  One CTA owns one env:
 //   * the env's FP64 integrator state lives in shared memory for the whole kernel
-//     (step, auto-reset burn-in and rasterise never round-trip through HBM),
+//     (step, auto-reset burn-in and rasterise never round-trip through HBM);
 //   * the O(N^2) pair forces run in FP32 on an FP32 hi/lo split of the positions staged in
-//     shared memory (broadcast LDS.128 = one source per load, T targets per thread in
-//     registers),
-//   * reward is a warp-shuffle + shared-memory reduction in FP64,
+//     shared memory.  For N <= 512 every UNORDERED pair is evaluated once (the pair force is
+//     exactly antisymmetric): a warp owns a 32-locust tile, walks the other tiles with a
+//     lane rotation, keeps its own forces in registers and hands the reaction forces round
+//     the warp with shuffles; reactions are combined through fixed shared-memory slots so
+//     the result is bitwise reproducible.  Larger N falls back to an ordered-pair loop with
+//     T targets per thread in registers and broadcast LDS.128 sources;
+//   * reward is a warp-shuffle + shared-memory reduction in FP64;
 //   * the occupancy grid is a shared-memory-privatised histogram with warp-aggregated
-//     atomics (match.any), written out as a streaming zero fill + sparse scatter.
+//     atomics (match.any), written out as a streaming zero fill + sparse scatter.  Its
+//     counter table aliases the force scratch (the two phases never overlap).
 //
 // Reference semantics restated here: fed_gym/envs/multiagent.py:30-115,
 // fed_gym/agents/state_processors.py:25-42.
@@ -19,11 +24,16 @@
 
 namespace swarm {
 
+constexpr int kSymMaxLocusts = 512;     // unordered-pair path (MODE 1) up to here
+constexpr unsigned kFull = 0xffffffffu;
+
 // Kernel-side parameter block (derived from SwarmParams on the host).
+// Pair geometry is done in coordinates pre-scaled by c = log2(e):  exp(-r) = 2^(-c r), and
+// d/(r + eps) is scale free if eps is scaled too, so the scaling costs nothing per pair.
 struct KP {
     int E, N, A, G, n_burn, max_steps;
-    double sigma, wind, dt, half_w, y_hi;
-    float F, negc1, negc2, invL, U, Gv, eps;
+    double sigma, wind, dt, half_w, y_hi, cscale;
+    float F, nInvL, U, Gv, eps_s;
     uint2 key;
     uint32_t env_off;
 };
@@ -33,36 +43,45 @@ struct Smem {
     double2* as;      // A   agent positions
     double2* act;     // A   current actions
     double2* an;      // A   current agent noise row (unscaled)
-    float4* src;      // N+A FP32 sources as (hi_x, hi_y, lo_x, lo_y): x = hi + lo to ~2^-48
     double* red;      // 32  reduction scratch
     double* box;      // 2   rasteriser: mean x
+    // ---- scratch, aliased between the force phase and the rasteriser
+    float4* src;      // FP32 sources (hi_x, hi_y, lo_x, lo_y), x = hi + lo to ~2^-48.
+                      //   MODE 1: nt tiles x 64 (each 32-tile stored twice: wrap-free lane+k reads) + A agents
+                      //   MODE 2/4: N locusts + A agents
+    float2* slot;     // MODE 1: nt x (1 + nt/2) x 32 reaction-force partial sums
     uint32_t* table;  // G*G packed cell counters: lo16 locusts, hi16 agents
 };
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
+__host__ __device__ inline int n_tiles(int N) { return (N + 31) >> 5; }
 
-__host__ __device__ inline size_t smem_bytes(int N, int A, int G, bool raster) {
-    size_t b = 0;
-    b += smem_align(sizeof(double2) * N);
-    b += 3 * smem_align(sizeof(double2) * A);
-    b += smem_align(sizeof(float4) * (N + A));
-    b += smem_align(sizeof(double) * 32);
-    b += smem_align(sizeof(double) * 2);
-    if (raster) b += smem_align(sizeof(uint32_t) * G * G);
-    return b;
+__host__ __device__ inline size_t smem_src_bytes(int N, int A, bool sym) {
+    return smem_align(sizeof(float4) * (sym ? (size_t)n_tiles(N) * 64 + A : (size_t)N + A));
+}
+__host__ __device__ inline size_t smem_fixed_bytes(int N, int A) {
+    return smem_align(sizeof(double2) * N) + 3 * smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) +
+           smem_align(sizeof(double) * 2);
+}
+__host__ __device__ inline size_t smem_bytes(int N, int A, int G, bool raster, bool sym) {
+    const int nt = n_tiles(N);
+    size_t force = smem_src_bytes(N, A, sym) + (sym ? smem_align(sizeof(float2) * nt * (1 + nt / 2) * 32) : 0);
+    size_t rast = raster ? smem_align(sizeof(uint32_t) * G * G) : 0;
+    return smem_fixed_bytes(N, A) + (force > rast ? force : rast);
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, bool raster) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, bool sym) {
     Smem s;
     size_t o = 0;
     s.xs = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * N);
     s.as = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
     s.act = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * A);
     s.an = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
-    s.src = reinterpret_cast<float4*>(base + o);  o += smem_align(sizeof(float4) * (N + A));
     s.red = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 32);
     s.box = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 2);
-    s.table = raster ? reinterpret_cast<uint32_t*>(base + o) : nullptr;
+    s.src = reinterpret_cast<float4*>(base + o);
+    s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
+    s.table = reinterpret_cast<uint32_t*>(base + o);
     return s;
 }
 
@@ -82,79 +101,179 @@ __device__ __forceinline__ void move_particle(double2& p, double2 v, double2 n, 
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
 }
 
 // ------------------------------------------------------------------------------------------
-// One ordered pair (source i -> target j), multiagent.py:65-68,100-113:
-//   w = s(r)/(r+eps), s(r) = F exp(-r/L) - exp(-r);  acc += w * (x_i - x_j)
+// Pair weight, multiagent.py:65-68,100-113:  w = s(r)/(r+eps), s(r) = F exp(-r/L) - exp(-r),
+// in log2(e)-scaled coordinates:  w = (F 2^(-r/L) - 2^(-r)) / (r + c eps).
 // Positions arrive as FP32 hi/lo pairs of the FP64 state, so the difference
 //   d = (hi_i - hi_j) + (lo_i - lo_j)
 // carries ~2^-24 RELATIVE error however close the two particles are (plain FP32 positions lose
-// the direction of close pairs, where s/(r+eps) is steepest).  The self pair (and any coincident
-// pair) has d = 0 exactly and contributes exactly 0.
+// the direction of close pairs, where s/(r+eps) is steepest).  Coincident points (and the self
+// pair of the ordered loop) have d = 0 exactly and contribute exactly 0.
 template <bool PRECISE>
-__device__ __forceinline__ void pair_force(const float4 q, const float4 tg, const KP& kp, float& ax, float& ay) {
-    const float dx = (q.x - tg.x) + (q.z - tg.z);
-    const float dy = (q.y - tg.y) + (q.w - tg.w);
+__device__ __forceinline__ float pair_weight(const float dx, const float dy, const KP& kp) {
     if (PRECISE) {
         const float r = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-        const float s = __fmaf_rn(kp.F, expf(-r * kp.invL), -expf(-r));
-        const float w = __fdiv_rn(s, __fadd_rn(r, kp.eps));
-        ax = __fmaf_rn(w, dx, ax);
-        ay = __fmaf_rn(w, dy, ay);
+        const float s = __fmaf_rn(kp.F, exp2f(__fmul_rn(r, kp.nInvL)), -exp2f(-r));
+        return __fdiv_rn(s, __fadd_rn(r, kp.eps_s));
     } else {
         // r2 >= 1e-30 keeps rsqrt finite for coincident points (their dx,dy are 0 anyway)
         const float r2 = fmaf(dx, dx, fmaf(dy, dy, 1e-30f));
         float rinv, e1, e2, inv;
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
         const float r = r2 * rinv;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(r * kp.negc1));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(r * kp.negc2));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-r));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(r * kp.nInvL));
         const float s = fmaf(kp.F, e2, -e1);
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + kp.eps));
-        const float w = s * inv;
-        ax = fmaf(w, dx, ax);
-        ay = fmaf(w, dy, ay);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + kp.eps_s));
+        return s * inv;
     }
 }
 
-__device__ __forceinline__ float4 split_hilo(const double2 p) {
-    const float hx = (float)p.x, hy = (float)p.y;
-    return make_float4(hx, hy, (float)(p.x - (double)hx), (float)(p.y - (double)hy));
+// ordered pair: force of source q on target tg
+template <bool PRECISE>
+__device__ __forceinline__ void pair_ordered(const float4 q, const float4 tg, const KP& kp, float& ax, float& ay) {
+    const float dx = (q.x - tg.x) + (q.z - tg.z);
+    const float dy = (q.y - tg.y) + (q.w - tg.w);
+    const float w = pair_weight<PRECISE>(dx, dy, kp);
+    ax = fmaf(w, dx, ax);
+    ay = fmaf(w, dy, ay);
 }
 
-// Stage the FP32 hi/lo sources: locusts then agents.
-__device__ __forceinline__ void stage_sources(const Smem& sm, int N, int A) {
-    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.src[i] = split_hilo(sm.xs[i]);
-    for (int k = threadIdx.x; k < A; k += blockDim.x) sm.src[N + k] = split_hilo(sm.as[k]);
+__device__ __forceinline__ float4 split_hilo(const double2 p, const double c) {
+    const double sx = p.x * c, sy = p.y * c;
+    const float hx = (float)sx, hy = (float)sy;
+    return make_float4(hx, hy, (float)(sx - (double)hx), (float)(sy - (double)hy));
 }
 
-// All-pairs forces for this thread's T targets (j = tid + t*blockDim.x); returns pre-cutoff v
-// (wind and gravity added) and the block-wide reward = -mean_j |v_j|^2.
+// Stage the scaled FP32 hi/lo sources: locusts then agents.
+template <int MODE>
+__device__ __forceinline__ void stage_sources(const Smem& sm, const KP& kp) {
+    const int N = kp.N, A = kp.A;
+    if (MODE == 1) {
+        const int nt = n_tiles(N);
+        // pad lanes sit far away: as sources they contribute exactly 0 (both exponentials underflow)
+        const float4 pad = make_float4(1e15f, 0.f, 0.f, 0.f);
+        for (int j = threadIdx.x; j < nt * 32; j += blockDim.x) {
+            const float4 q = j < N ? split_hilo(sm.xs[j], kp.cscale) : pad;
+            float4* t = sm.src + (j >> 5) * 64 + (j & 31);
+            t[0] = q;
+            t[32] = q;
+        }
+        for (int k = threadIdx.x; k < A; k += blockDim.x) sm.src[nt * 64 + k] = split_hilo(sm.as[k], kp.cscale);
+    } else {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) sm.src[i] = split_hilo(sm.xs[i], kp.cscale);
+        for (int k = threadIdx.x; k < A; k += blockDim.x) sm.src[N + k] = split_hilo(sm.as[k], kp.cscale);
+    }
+}
+
+// Rotation steps K0..K1 of one tile pair: in step k lane l meets element (l+k)%32 of the other
+// tile (read wrap-free from the doubled tile).  The own force accumulates in (ax,ay); the
+// reaction on the met element accumulates in (bx,by), which moves one lane down per step so
+// that it follows its element.  On return lane l holds the reaction for element (l+K1)%32.
+template <int K0, int K1, bool PRECISE>
+__device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const float4 tg, const KP& kp, const int nxt,
+                                         float& ax, float& ay, float& bx, float& by) {
+    bx = 0.f;
+    by = 0.f;
+#pragma unroll
+    for (int k = K0; k <= K1; ++k) {
+        const float4 q = tl[k];
+        const float dx = (q.x - tg.x) + (q.z - tg.z);
+        const float dy = (q.y - tg.y) + (q.w - tg.w);
+        const float w = pair_weight<PRECISE>(dx, dy, kp);
+        ax = fmaf(w, dx, ax);
+        ay = fmaf(w, dy, ay);
+        bx = fmaf(-w, dx, bx);
+        by = fmaf(-w, dy, by);
+        if (k < K1) {
+            bx = __shfl_sync(kFull, bx, nxt);
+            by = __shfl_sync(kFull, by, nxt);
+        }
+    }
+}
+
+// MODE 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I meets
+// tiles I+1..I+floor((nt-1)/2) fully, tile I+nt/2 (nt even) half each way, and itself.
+template <bool PRECISE>
+__device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, float& ax, float& ay) {
+    const int lane = threadIdx.x & 31, I = threadIdx.x >> 5;
+    const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
+    const int nxt = (lane + 1) & 31;
+    const float4* S = sm.src;
+    const float4 tg = S[I * 64 + lane];
+    float bx, by;
+    ax = 0.f;
+    ay = 0.f;
+    // own tile: offsets 1..15 both ways, offset 16 one way (each such pair appears in two lanes), offset 0 = self
+    tile_sym<1, 15, PRECISE>(S + I * 64 + lane, tg, kp, nxt, ax, ay, bx, by);
+    sm.slot[(I * nslots) * 32 + ((lane + 15) & 31)] = make_float2(bx, by);
+    pair_ordered<PRECISE>(S[I * 64 + lane + 16], tg, kp, ax, ay);
+    const int nfull = (nt - 1) >> 1;
+    for (int o = 1; o <= nfull; ++o) {
+        int B = I + o;
+        if (B >= nt) B -= nt;
+        tile_sym<0, 31, PRECISE>(S + B * 64 + lane, tg, kp, nxt, ax, ay, bx, by);
+        sm.slot[(B * nslots + o) * 32 + ((lane + 31) & 31)] = make_float2(bx, by);
+    }
+    if ((nt & 1) == 0) {
+        // lane offsets 0..15 from the lower tile, 16..31 (= 1..16 seen from the partner) from the upper
+        const int o = nt >> 1;
+        const int B = I < o ? I + o : I - o;
+        const int koff = I < o ? 0 : 1;
+        tile_sym<0, 15, PRECISE>(S + B * 64 + lane + koff, tg, kp, nxt, ax, ay, bx, by);
+        sm.slot[(B * nslots + o) * 32 + ((lane + 15 + koff) & 31)] = make_float2(bx, by);
+    }
+    __syncthreads();
+    for (int o = 0; o < nslots; ++o) {          // fixed order: bitwise reproducible
+        const float2 r = sm.slot[(I * nslots + o) * 32 + lane];
+        ax += r.x;
+        ay += r.y;
+    }
+    const float4* ag = S + nt * 64;             // agents act on locusts only (multiagent.py:108-113)
+    for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, ax, ay);
+}
+
+// MODE 2/4: ordered pairs, T targets per thread (j = tid + t*blockDim.x), broadcast LDS.128 sources.
 template <int T, bool PRECISE>
-__device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, float (&vx)[T], float (&vy)[T]) {
+__device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, float (&vx)[T], float (&vy)[T]) {
     const int N = kp.N, S = kp.N + kp.A;
     float4 tg[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int j = threadIdx.x + t * blockDim.x;
         tg[t] = sm.src[j < N ? j : N - 1];
-        vx[t] = 0.f; vy[t] = 0.f;
+        vx[t] = 0.f;
+        vy[t] = 0.f;
     }
 #pragma unroll 4
     for (int i = 0; i < S; ++i) {
-        const float4 q = sm.src[i];              // broadcast LDS.128: one source for the whole warp
+        const float4 q = sm.src[i];
 #pragma unroll
-        for (int t = 0; t < T; ++t) pair_force<PRECISE>(q, tg[t], kp, vx[t], vy[t]);
+        for (int t = 0; t < T; ++t) pair_ordered<PRECISE>(q, tg[t], kp, vx[t], vy[t]);
     }
+}
+
+template <int MODE>
+struct ModeT { static constexpr int T = MODE == 1 ? 1 : MODE; };
+
+// Forces on this thread's targets + block-wide reward = -mean_j |v_j|^2 (pre-cutoff v, wind and
+// gravity added).  Needs the staged sources visible; ends after a barrier.
+template <int MODE, bool PRECISE>
+__device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, float (&vx)[ModeT<MODE>::T],
+                                              float (&vy)[ModeT<MODE>::T]) {
+    constexpr int T = ModeT<MODE>::T;
+    if (MODE == 1) forces_sym<PRECISE>(sm, kp, vx[0], vy[0]);
+    else forces_ordered<T, PRECISE>(sm, kp, vx, vy);
     double e = 0.0;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         vx[t] += kp.U;
         vy[t] += kp.Gv;
-        if (threadIdx.x + t * blockDim.x < N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
+        if (threadIdx.x + t * blockDim.x < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
     }
     e = warp_sum(e);
     if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = e;
@@ -162,14 +281,16 @@ __device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, floa
     double tot = 0.0;
     const int nw = (blockDim.x + 31) >> 5;
     for (int w = 0; w < nw; ++w) tot += sm.red[w];   // same order in every thread
-    return -tot / (double)N;
+    return -tot / (double)kp.N;
 }
 
 // SwarmEnv._step on the shared-memory state.  Preconditions: sm.xs/as/act/an filled and
 // visible (a __syncthreads since their last write); nx[t] = unscaled noise of own target t.
-// Postcondition: state updated and visible to the whole block.
-template <int T, bool PRECISE>
-__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const double2 (&nx)[T], float* v_out) {
+// Postcondition: state updated and visible to the whole block; force scratch free again.
+template <int MODE, bool PRECISE>
+__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const double2 (&nx)[ModeT<MODE>::T],
+                                           float* v_out) {
+    constexpr int T = ModeT<MODE>::T;
     // multiagent.py:33-38  agents move first: v_action (+wind on x) through x_update
     for (int k = threadIdx.x; k < kp.A; k += blockDim.x) {
         double2 a = sm.as[k];
@@ -179,10 +300,10 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const d
         sm.as[k] = a;
     }
     __syncthreads();
-    stage_sources(sm, kp.N, kp.A);       // old x, NEW xa (multiagent.py:39)
+    stage_sources<MODE>(sm, kp);         // old x, NEW xa (multiagent.py:39)
     __syncthreads();
     float vx[T], vy[T];
-    const double reward = pair_forces<T, PRECISE>(sm, kp, vx, vy);
+    const double reward = pair_forces<MODE, PRECISE>(sm, kp, vx, vy);
     // multiagent.py:40  locusts move with the pre-cutoff v just computed
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -200,9 +321,10 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const d
 
 // SwarmEnv._reset (multiagent.py:46-63) for env e: draws (injected or Philox), n_burn burn-in
 // steps with noise row k, then the frozen row n_burn is stored for all later steps (Q1).
-template <int T, bool PRECISE>
-__device__ __forceinline__ void env_reset(const Smem& sm, const KP& kp, int e, uint32_t episode,
-                                          const bool inj, const SwarmInjectedDraws& dr, const SwarmState& st) {
+template <int MODE, bool PRECISE>
+__device__ __noinline__ void env_reset(const Smem& sm, const KP& kp, int e, uint32_t episode, const bool inj,
+                                       const SwarmInjectedDraws& dr, const SwarmState& st) {
+    constexpr int T = ModeT<MODE>::T;
     const int N = kp.N, A = kp.A;
     DrawCtx ctx;
     ctx.key = kp.key;
@@ -244,7 +366,7 @@ __device__ __forceinline__ void env_reset(const Smem& sm, const KP& kp, int e, u
                            : draw_normal2(ctx, STREAM_NOISE_A, r, k);
         }
         __syncthreads();
-        env_step<T, PRECISE>(sm, kp, nx, nullptr);
+        env_step<MODE, PRECISE>(sm, kp, nx, nullptr);
     }
     __syncthreads();
 }
@@ -267,6 +389,7 @@ __device__ __forceinline__ int count_le(double p, double lo, double hi, double s
 
 // SwarmStateProcessor.process_state (state_processors.py:25-42) of the shared-memory state.
 // MAXIT >= ceil((N+A)/blockDim.x).  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
+// Uses sm.table, i.e. the force scratch must be dead (a barrier since its last use).
 template <int MAXIT>
 __device__ __forceinline__ void env_raster(const Smem& sm, const KP& kp, float* __restrict__ grid_e,
                                            uint8_t* __restrict__ pos_e) {
@@ -328,7 +451,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const KP& kp, float* 
                 key = ((uint32_t)cell << 1) | (agent ? 1u : 0u);
             }
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t peers = __match_any_sync(kFull, key);
         if (key != 0xffffffffu && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
             const uint32_t inc = (uint32_t)__popc(peers) << ((key & 1u) ? 16 : 0);
             const uint32_t old = atomicAdd(&sm.table[cell], inc);
