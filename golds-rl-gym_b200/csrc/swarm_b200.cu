@@ -22,7 +22,12 @@ __global__ void __launch_bounds__(512, 2) k_step(const KP kp, const SwarmState s
     const int N = kp.N, A = kp.A;
     constexpr int T = ModeT<MODE>::T;
     const bool raster = io.grid != nullptr;
-    const Smem sm = carve(smem_raw, N, A, MODE == 1);
+    const Smem sm = carve(smem_raw, N, A, kp.G, MODE == 1);
+    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
+    float* grid_e = raster ? io.grid + (size_t)e * kp.G * kp.G * 2 : nullptr;
+    // The observation is ~99 % zeros: stream them out first, so the stores drain to HBM under
+    // the force phase; the non-zero cells are scattered over them at the end.
+    if (raster) raster_zero_fill(grid_e, kp.G * kp.G, g.tid, g.n);
 
     // state -> shared memory: one double2 (LDG.128) per particle, fully coalesced
     const double2* gx = reinterpret_cast<const double2*>(st.x) + (size_t)e * N;
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(512, 2) k_step(const KP kp, const SwarmState s
     }
     __syncthreads();
 
-    const double reward = env_step<MODE, PRECISE>(sm, kp, nx, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
+    const double reward = env_step<MODE, PRECISE>(sm, kp, g, nx, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
 
     // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
     int elapsed = st.elapsed[e] + 1;
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(512, 2) k_step(const KP kp, const SwarmState s
         // emulator_runner.py:127-132: the terminal reward/done are reported, the state (and
         // therefore the observation) is the freshly reset episode's.  Block-uniform branch.
         const uint32_t ep = st.episode[e];
-        env_reset<MODE, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
+        env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
         elapsed = 0;
         if (threadIdx.x == 0) st.episode[e] = ep + 1;
     }
@@ -94,8 +99,7 @@ __global__ void __launch_bounds__(512, 2) k_step(const KP kp, const SwarmState s
     for (int i = threadIdx.x; i < N; i += blockDim.x) ox[i] = sm.xs[i];
     for (int k = threadIdx.x; k < A; k += blockDim.x) oa[k] = sm.as[k];
 
-    if (raster)
-        env_raster<T + 1>(sm, kp, io.grid + (size_t)e * kp.G * kp.G * 2, io.positions + (size_t)e * A * 2);
+    if (raster) env_raster(sm, sm.xs, sm.as, kp, g, grid_e, io.positions + (size_t)e * A * 2);
 }
 
 // SwarmEnv._reset for the masked envs.
@@ -105,9 +109,10 @@ __global__ void __launch_bounds__(512, 2) k_reset(const KP kp, const SwarmState 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, MODE == 1);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, MODE == 1);
+    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const uint32_t ep = st.episode[e];
-    env_reset<MODE, PRECISE>(sm, kp, e, ep, has_draws != 0, dr, st);
+    env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
     double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * kp.N;
     double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * kp.A;
     for (int i = threadIdx.x; i < kp.N; i += blockDim.x) ox[i] = sm.xs[i];
@@ -125,14 +130,16 @@ __global__ void __launch_bounds__(512, 2) k_rasterize(const KP kp, const double*
                                                    uint8_t* __restrict__ positions, double* __restrict__ box) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
-    constexpr int T = ModeT<MODE>::T;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, MODE == 1);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, MODE == 1);
+    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
+    float* grid_e = grid + (size_t)e * kp.G * kp.G * 2;
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
     for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
     for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
+    raster_zero_fill(grid_e, kp.G * kp.G, g.tid, g.n);
     __syncthreads();
-    env_raster<T + 1>(sm, kp, grid + (size_t)e * kp.G * kp.G * 2, positions + (size_t)e * kp.A * 2);
+    env_raster(sm, sm.xs, sm.as, kp, g, grid_e, positions + (size_t)e * kp.A * 2);
     if (box && threadIdx.x == 0) {       // sm.box[0] was published before env_raster's first barrier
         const double m = sm.box[0];
         box[4 * e + 0] = m - kp.half_w;
@@ -150,16 +157,17 @@ __global__ void __launch_bounds__(512, 2) k_forces(const KP kp, const double* __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     constexpr int T = ModeT<MODE>::T;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, MODE == 1);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, MODE == 1);
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
     for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
     for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
     __syncthreads();
-    stage_sources<MODE>(sm, kp);
+    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
+    stage_sources<MODE>(sm, kp, g);
     __syncthreads();
     float vx[T], vy[T];
-    const double r = pair_forces<MODE, PRECISE>(sm, kp, vx, vy);
+    const double r = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
     if (v) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {

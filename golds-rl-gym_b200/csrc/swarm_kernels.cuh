@@ -51,6 +51,7 @@ struct Smem {
                       //   MODE 2/4: N locusts + A agents
     float2* slot;     // MODE 1: nt x (1 + nt/2) x 32 reaction-force partial sums
     uint32_t* table;  // G*G packed cell counters: lo16 locusts, hi16 agents
+    int* cid;         // N+A: cell written out by this point (or -1)
 };
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
@@ -63,14 +64,17 @@ __host__ __device__ inline size_t smem_fixed_bytes(int N, int A) {
     return smem_align(sizeof(double2) * N) + 3 * smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) +
            smem_align(sizeof(double) * 2);
 }
+__host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G) {
+    return smem_align(sizeof(uint32_t) * G * G) + smem_align(sizeof(int) * (N + A));
+}
 __host__ __device__ inline size_t smem_bytes(int N, int A, int G, bool raster, bool sym) {
     const int nt = n_tiles(N);
     size_t force = smem_src_bytes(N, A, sym) + (sym ? smem_align(sizeof(float2) * nt * (1 + nt / 2) * 32) : 0);
-    size_t rast = raster ? smem_align(sizeof(uint32_t) * G * G) : 0;
+    size_t rast = raster ? smem_raster_bytes(N, A, G) : 0;
     return smem_fixed_bytes(N, A) + (force > rast ? force : rast);
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, bool sym) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, bool sym) {
     Smem s;
     size_t o = 0;
     s.xs = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * N);
@@ -82,6 +86,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, bool sy
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
     s.table = reinterpret_cast<uint32_t*>(base + o);
+    s.cid = reinterpret_cast<int*>(base + o + smem_align(sizeof(uint32_t) * G * G));
     return s;
 }
 
@@ -98,6 +103,13 @@ __device__ __forceinline__ void move_particle(double2& p, double2 v, double2 n, 
     p.y = __dadd_rn(p.y, __dadd_rn(__dmul_rn(dt, v.y), __dmul_rn(sigma, n.y)));
     if (p.y <= 0.0) p.y = 0.0;
 }
+
+// The threads that cooperate on one env (today: the whole CTA).
+struct Grp {
+    int tid;   // thread index inside the group
+    int n;     // threads in the group (multiple of 32)
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -151,22 +163,22 @@ __device__ __forceinline__ float4 split_hilo(const double2 p, const double c) {
 
 // Stage the scaled FP32 hi/lo sources: locusts then agents.
 template <int MODE>
-__device__ __forceinline__ void stage_sources(const Smem& sm, const KP& kp) {
+__device__ __forceinline__ void stage_sources(const Smem& sm, const KP& kp, const Grp& g) {
     const int N = kp.N, A = kp.A;
     if (MODE == 1) {
         const int nt = n_tiles(N);
         // pad lanes sit far away: as sources they contribute exactly 0 (both exponentials underflow)
         const float4 pad = make_float4(1e15f, 0.f, 0.f, 0.f);
-        for (int j = threadIdx.x; j < nt * 32; j += blockDim.x) {
+        for (int j = g.tid; j < nt * 32; j += g.n) {
             const float4 q = j < N ? split_hilo(sm.xs[j], kp.cscale) : pad;
             float4* t = sm.src + (j >> 5) * 64 + (j & 31);
             t[0] = q;
             t[32] = q;
         }
-        for (int k = threadIdx.x; k < A; k += blockDim.x) sm.src[nt * 64 + k] = split_hilo(sm.as[k], kp.cscale);
+        for (int k = g.tid; k < A; k += g.n) sm.src[nt * 64 + k] = split_hilo(sm.as[k], kp.cscale);
     } else {
-        for (int i = threadIdx.x; i < N; i += blockDim.x) sm.src[i] = split_hilo(sm.xs[i], kp.cscale);
-        for (int k = threadIdx.x; k < A; k += blockDim.x) sm.src[N + k] = split_hilo(sm.as[k], kp.cscale);
+        for (int i = g.tid; i < N; i += g.n) sm.src[i] = split_hilo(sm.xs[i], kp.cscale);
+        for (int k = g.tid; k < A; k += g.n) sm.src[N + k] = split_hilo(sm.as[k], kp.cscale);
     }
 }
 
@@ -199,8 +211,8 @@ __device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const fl
 // MODE 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I meets
 // tiles I+1..I+floor((nt-1)/2) fully, tile I+nt/2 (nt even) half each way, and itself.
 template <bool PRECISE>
-__device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, float& ax, float& ay) {
-    const int lane = threadIdx.x & 31, I = threadIdx.x >> 5;
+__device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
     const int nxt = (lane + 1) & 31;
     const float4* S = sm.src;
@@ -227,7 +239,7 @@ __device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, float& 
         tile_sym<0, 15, PRECISE>(S + B * 64 + lane + koff, tg, kp, nxt, ax, ay, bx, by);
         sm.slot[(B * nslots + o) * 32 + ((lane + 15 + koff) & 31)] = make_float2(bx, by);
     }
-    __syncthreads();
+    g.sync();
     for (int o = 0; o < nslots; ++o) {          // fixed order: bitwise reproducible
         const float2 r = sm.slot[(I * nslots + o) * 32 + lane];
         ax += r.x;
@@ -239,12 +251,12 @@ __device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, float& 
 
 // MODE 2/4: ordered pairs, T targets per thread (j = tid + t*blockDim.x), broadcast LDS.128 sources.
 template <int T, bool PRECISE>
-__device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, float (&vx)[T], float (&vy)[T]) {
+__device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[T], float (&vy)[T]) {
     const int N = kp.N, S = kp.N + kp.A;
     float4 tg[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const int j = threadIdx.x + t * blockDim.x;
+        const int j = g.tid + t * g.n;
         tg[t] = sm.src[j < N ? j : N - 1];
         vx[t] = 0.f;
         vy[t] = 0.f;
@@ -263,23 +275,23 @@ struct ModeT { static constexpr int T = MODE == 1 ? 1 : MODE; };
 // Forces on this thread's targets + block-wide reward = -mean_j |v_j|^2 (pre-cutoff v, wind and
 // gravity added).  Needs the staged sources visible; ends after a barrier.
 template <int MODE, bool PRECISE>
-__device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, float (&vx)[ModeT<MODE>::T],
-                                              float (&vy)[ModeT<MODE>::T]) {
+__device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, const Grp& g,
+                                              float (&vx)[ModeT<MODE>::T], float (&vy)[ModeT<MODE>::T]) {
     constexpr int T = ModeT<MODE>::T;
-    if (MODE == 1) forces_sym<PRECISE>(sm, kp, vx[0], vy[0]);
-    else forces_ordered<T, PRECISE>(sm, kp, vx, vy);
+    if (MODE == 1) forces_sym<PRECISE>(sm, kp, g, vx[0], vy[0]);
+    else forces_ordered<T, PRECISE>(sm, kp, g, vx, vy);
     double e = 0.0;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         vx[t] += kp.U;
         vy[t] += kp.Gv;
-        if (threadIdx.x + t * blockDim.x < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
+        if (g.tid + t * g.n < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
     }
     e = warp_sum(e);
-    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = e;
-    __syncthreads();
+    if ((g.tid & 31) == 0) sm.red[g.tid >> 5] = e;
+    g.sync();
     double tot = 0.0;
-    const int nw = (blockDim.x + 31) >> 5;
+    const int nw = g.n >> 5;
     for (int w = 0; w < nw; ++w) tot += sm.red[w];   // same order in every thread
     return -tot / (double)kp.N;
 }
@@ -288,26 +300,26 @@ __device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, floa
 // visible (a __syncthreads since their last write); nx[t] = unscaled noise of own target t.
 // Postcondition: state updated and visible to the whole block; force scratch free again.
 template <int MODE, bool PRECISE>
-__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const double2 (&nx)[ModeT<MODE>::T],
-                                           float* v_out) {
+__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const Grp& g,
+                                           const double2 (&nx)[ModeT<MODE>::T], float* v_out) {
     constexpr int T = ModeT<MODE>::T;
     // multiagent.py:33-38  agents move first: v_action (+wind on x) through x_update
-    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) {
+    for (int k = g.tid; k < kp.A; k += g.n) {
         double2 a = sm.as[k];
         double2 w = sm.act[k];
         w.x = __dadd_rn(w.x, kp.wind);
         move_particle(a, w, sm.an[k], kp.dt, kp.sigma);
         sm.as[k] = a;
     }
-    __syncthreads();
-    stage_sources<MODE>(sm, kp);         // old x, NEW xa (multiagent.py:39)
-    __syncthreads();
+    g.sync();
+    stage_sources<MODE>(sm, kp, g);      // old x, NEW xa (multiagent.py:39)
+    g.sync();
     float vx[T], vy[T];
-    const double reward = pair_forces<MODE, PRECISE>(sm, kp, vx, vy);
+    const double reward = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
     // multiagent.py:40  locusts move with the pre-cutoff v just computed
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const int j = threadIdx.x + t * blockDim.x;
+        const int j = g.tid + t * g.n;
         if (j < kp.N) {
             if (v_out) reinterpret_cast<float2*>(v_out)[j] = make_float2(vx[t], vy[t]);
             double2 p = sm.xs[j];
@@ -315,25 +327,25 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const d
             sm.xs[j] = p;
         }
     }
-    __syncthreads();
+    g.sync();
     return reward;
 }
 
 // SwarmEnv._reset (multiagent.py:46-63) for env e: draws (injected or Philox), n_burn burn-in
 // steps with noise row k, then the frozen row n_burn is stored for all later steps (Q1).
 template <int MODE, bool PRECISE>
-__device__ __noinline__ void env_reset(const Smem& sm, const KP& kp, int e, uint32_t episode, const bool inj,
-                                       const SwarmInjectedDraws& dr, const SwarmState& st) {
+__device__ __noinline__ void env_reset(const Smem& sm, const KP& kp, const Grp& g, int e, uint32_t episode,
+                                       const bool inj, const SwarmInjectedDraws& dr, const SwarmState& st) {
     constexpr int T = ModeT<MODE>::T;
     const int N = kp.N, A = kp.A;
     DrawCtx ctx;
     ctx.key = kp.key;
     ctx.env = kp.env_off + (uint32_t)e;
     ctx.episode = episode;
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
+    for (int i = g.tid; i < N; i += g.n)
         sm.xs[i] = inj ? reinterpret_cast<const double2*>(dr.x0)[(size_t)e * N + i]
                        : draw_uniform2(ctx, STREAM_X0, i);
-    for (int k = threadIdx.x; k < A; k += blockDim.x)
+    for (int k = g.tid; k < A; k += g.n)
         sm.as[k] = inj ? reinterpret_cast<const double2*>(dr.xa0)[(size_t)e * A + k]
                        : draw_uniform2(ctx, STREAM_XA0, k);
     const int rows = kp.n_burn + 1;
@@ -341,7 +353,7 @@ __device__ __noinline__ void env_reset(const Smem& sm, const KP& kp, int e, uint
         double2 nx[T];
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const int j = threadIdx.x + t * blockDim.x;
+            const int j = g.tid + t * g.n;
             nx[t] = make_double2(0.0, 0.0);
             if (j < N)
                 nx[t] = inj ? reinterpret_cast<const double2*>(dr.particle_noise)[((size_t)e * rows + r) * N + j]
@@ -350,25 +362,25 @@ __device__ __noinline__ void env_reset(const Smem& sm, const KP& kp, int e, uint
         if (r == kp.n_burn) {   // frozen row: kept in HBM for every later step
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const int j = threadIdx.x + t * blockDim.x;
+                const int j = g.tid + t * g.n;
                 if (j < N) reinterpret_cast<double2*>(st.noise_x)[(size_t)e * N + j] = nx[t];
             }
-            for (int k = threadIdx.x; k < A; k += blockDim.x)
+            for (int k = g.tid; k < A; k += g.n)
                 reinterpret_cast<double2*>(st.noise_a)[(size_t)e * A + k] =
                     inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
                         : draw_normal2(ctx, STREAM_NOISE_A, r, k);
             break;
         }
-        for (int k = threadIdx.x; k < A; k += blockDim.x) {
+        for (int k = g.tid; k < A; k += g.n) {
             sm.act[k] = inj ? reinterpret_cast<const double2*>(dr.burn_actions)[((size_t)e * kp.n_burn + r) * A + k]
                             : draw_normal2(ctx, STREAM_BURN, r, k);
             sm.an[k] = inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
                            : draw_normal2(ctx, STREAM_NOISE_A, r, k);
         }
-        __syncthreads();
-        env_step<MODE, PRECISE>(sm, kp, nx, nullptr);
+        g.sync();
+        env_step<MODE, PRECISE>(sm, kp, g, nx, nullptr);
     }
-    __syncthreads();
+    g.sync();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -378,68 +390,63 @@ __device__ __forceinline__ double edge_at(int i, double lo, double hi, double st
     return i >= G ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
 }
 
-__device__ __forceinline__ int count_le(double p, double lo, double hi, double step, int G) {
+// The bin is guessed with a reciprocal multiply and then corrected against the exact edges.
+__device__ __forceinline__ int count_le(double p, double lo, double hi, double step, double inv_step, int G) {
     if (!(p == p)) return G + 1;                 // NaN sorts last
-    const double q = (p - lo) / step;
+    const double q = (p - lo) * inv_step;
     int g = q < -1.0 ? -1 : (q > (double)G ? G : (int)floor(q));
     while (g < G && edge_at(g + 1, lo, hi, step, G) <= p) ++g;
     while (g >= 0 && edge_at(g, lo, hi, step, G) > p) --g;
     return g + 1;                                // #{i in [0,G] : e[i] <= p}
 }
 
-// SwarmStateProcessor.process_state (state_processors.py:25-42) of the shared-memory state.
-// MAXIT >= ceil((N+A)/blockDim.x).  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
-// Uses sm.table, i.e. the force scratch must be dead (a barrier since its last use).
-template <int MAXIT>
-__device__ __forceinline__ void env_raster(const Smem& sm, const KP& kp, float* __restrict__ grid_e,
+// Streaming zero fill of one env's (G,G,2) f32 grid by n threads (evict-first stores).
+__device__ __forceinline__ void raster_zero_fill(float* __restrict__ grid_e, int cells, int tid, int n) {
+    if ((cells & 1) == 0) {
+        float4* g4 = reinterpret_cast<float4*>(grid_e);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < cells / 2; i += n) __stcs(g4 + i, z);
+    } else {
+        float2* g2 = reinterpret_cast<float2*>(grid_e);
+        for (int i = tid; i < cells; i += n) __stcs(g2 + i, make_float2(0.f, 0.f));
+    }
+}
+
+// SwarmStateProcessor.process_state (state_processors.py:25-42) of the positions xs (N) / as (A) in
+// shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
+// The grid must have been zero-filled (raster_zero_fill) before a barrier that precedes this call.
+// Uses sm.table / sm.cid / sm.box (the force scratch must be dead unless they do not alias).
+__device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ xs, const double2* __restrict__ as,
+                                           const KP& kp, const Grp& g, float* __restrict__ grid_e,
                                            uint8_t* __restrict__ pos_e) {
     const int N = kp.N, A = kp.A, G = kp.G, P = N + A, cells = G * G;
     // phase 0: one thread walks the sequential FP64 mean (np.mean(vstack([x,xa]),axis=0)[0] is a
-    // plain left-to-right sum); everyone else clears the counters and streams zeros to HBM.
-    if (threadIdx.x == 0) {
+    // plain left-to-right sum, ~23 cycles per dependent DADD); everyone else clears the counters.
+    if (g.tid == 0) {
         double s = 0.0;
-        for (int i = 0; i < N; ++i) s = __dadd_rn(s, sm.xs[i].x);
-        for (int k = 0; k < A; ++k) s = __dadd_rn(s, sm.as[k].x);
+        for (int i = 0; i < N; ++i) s = __dadd_rn(s, xs[i].x);
+        for (int k = 0; k < A; ++k) s = __dadd_rn(s, as[k].x);
         sm.box[0] = s / (double)P;
+    } else {
+        for (int i = g.tid - 1; i < cells; i += g.n - 1) sm.table[i] = 0u;
     }
-    {
-        const int first = blockDim.x > 32 ? 32 : 0;     // warp 0 is busy with the mean
-        const int nt = blockDim.x - first;
-        const int t = (int)threadIdx.x - first;
-        if (t >= 0) {
-            if ((cells & 1) == 0) {
-                float4* g4 = reinterpret_cast<float4*>(grid_e);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = t; i < cells / 2; i += nt) __stcs(g4 + i, z);
-            } else {
-                float2* g2 = reinterpret_cast<float2*>(grid_e);
-                for (int i = t; i < cells; i += nt) __stcs(g2 + i, make_float2(0.f, 0.f));
-            }
-        }
-        for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.table[i] = 0u;
-    }
-    __syncthreads();
+    g.sync();
     // phase 1: bin every point in FP64 against numpy's edges, count with warp-aggregated atomics
     const double m = sm.box[0];
     const double lo_x = m - kp.half_w, hi_x = m + kp.half_w;
     const double step_x = (hi_x - lo_x) / (double)G;
     const double lo_y = 0.0, hi_y = kp.y_hi;
     const double step_y = (hi_y - lo_y) / (double)G;
-    int wcell[MAXIT];
-#pragma unroll
-    for (int it = 0; it < MAXIT; ++it) wcell[it] = -1;
-#pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-        const int base = it * blockDim.x;
-        if (base >= P) break;
-        const int p = base + threadIdx.x;
+    const double inv_x = 1.0 / step_x, inv_y = 1.0 / step_y;
+    for (int base = 0; base < P; base += g.n) {
+        const int p = base + g.tid;
         uint32_t key = 0xffffffffu;
         int cell = 0;
         if (p < P) {
             const bool agent = p >= N;
-            const double2 q = agent ? sm.as[p - N] : sm.xs[p];
-            const int cx = count_le(q.x, lo_x, hi_x, step_x, G);
-            const int cy = count_le(q.y, lo_y, hi_y, step_y, G);
+            const double2 q = agent ? as[p - N] : xs[p];
+            const int cx = count_le(q.x, lo_x, hi_x, step_x, inv_x, G);
+            const int cy = count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
             if (agent) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
                 pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
                 pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
@@ -452,21 +459,23 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const KP& kp, float* 
             }
         }
         const uint32_t peers = __match_any_sync(kFull, key);
-        if (key != 0xffffffffu && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+        int mine = -1;
+        if (key != 0xffffffffu && (__ffs(peers) - 1) == (g.tid & 31)) {
             const uint32_t inc = (uint32_t)__popc(peers) << ((key & 1u) ? 16 : 0);
             const uint32_t old = atomicAdd(&sm.table[cell], inc);
-            if (old == 0u) wcell[it] = cell;          // first arrival writes the cell out
+            if (old == 0u) mine = cell;               // first arrival writes the cell out
         }
+        if (p < P) sm.cid[p] = mine;
     }
-    __syncthreads();
+    g.sync();
     // phase 2: sparse scatter of the non-zero cells over the zero fill
     float2* g2 = reinterpret_cast<float2*>(grid_e);
-#pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-        if (wcell[it] >= 0) {
-            const uint32_t w = sm.table[wcell[it]];
-            g2[wcell[it]] = make_float2(__fdiv_rn((float)(w & 0xffffu), (float)N),
-                                        A > 0 ? __fdiv_rn((float)(w >> 16), (float)A) : 0.f);
+    for (int p = g.tid; p < P; p += g.n) {
+        const int c = sm.cid[p];
+        if (c >= 0) {
+            const uint32_t w = sm.table[c];
+            g2[c] = make_float2(__fdiv_rn((float)(w & 0xffffu), (float)N),
+                                A > 0 ? __fdiv_rn((float)(w >> 16), (float)A) : 0.f);
         }
     }
 }
