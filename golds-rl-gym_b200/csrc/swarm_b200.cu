@@ -5,6 +5,11 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <utility>
+
 #include "swarm_kernels.cuh"
 
 using namespace swarm;
@@ -13,134 +18,190 @@ namespace {
 
 // ------------------------------------------------------------------------------------------ kernels
 
-// SwarmEnv._step + TimeLimit + SwarmRunner auto-reset + process_state, one CTA per env.
-template <int MODE, bool PRECISE>
-__global__ void __launch_bounds__(512, 2) k_step(const KP kp, const SwarmState st, const SwarmStepIO io,
-                                              const SwarmInjectedDraws dr, const int has_draws) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int e = blockIdx.x;
+// Issue the cp.async copies of everything env e's step reads from HBM into stage buffer sg.
+__device__ __forceinline__ void prefetch_env(const Stage& sg, const KP& kp, const SwarmState& st, const SwarmStepIO& io,
+                                             const int e, const Grp& g) {
     const int N = kp.N, A = kp.A;
-    constexpr int T = ModeT<MODE>::T;
-    const bool raster = io.grid != nullptr;
-    const Smem sm = carve(smem_raw, N, A, kp.G, MODE == 1);
-    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
-    float* grid_e = raster ? io.grid + (size_t)e * kp.G * kp.G * 2 : nullptr;
-    // The observation is ~99 % zeros: stream them out first, so the stores drain to HBM under
-    // the force phase; the non-zero cells are scattered over them at the end.
-    if (raster) raster_zero_fill(grid_e, kp.G * kp.G, g.tid, g.n);
-
-    // state -> shared memory: one double2 (LDG.128) per particle, fully coalesced
     const double2* gx = reinterpret_cast<const double2*>(st.x) + (size_t)e * N;
+    const double2* gnx = reinterpret_cast<const double2*>(io.noise_x ? io.noise_x : st.noise_x) + (size_t)e * N;
+    for (int i = g.tid; i < N; i += g.n) {
+        cp_async<16>(sg.xs + i, gx + i);
+        cp_async<16>(sg.nx + i, gnx + i);
+    }
     const double2* ga = reinterpret_cast<const double2*>(st.xa) + (size_t)e * A;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.xs[i] = gx[i];
     const double2* gna = reinterpret_cast<const double2*>(io.noise_a ? io.noise_a : st.noise_a) + (size_t)e * A;
-    for (int k = threadIdx.x; k < A; k += blockDim.x) {
-        sm.as[k] = ga[k];
-        sm.an[k] = gna[k];
-        double2 a;
-        if (io.flags & SWARM_STEP_ACTIONS_F64) {
-            a = reinterpret_cast<const double2*>(io.actions_f64)[(size_t)e * A + k];
-        } else {
-            const float2 f = reinterpret_cast<const float2*>(io.actions_f32)[(size_t)e * A + k];
-            a = make_double2((double)f.x, (double)f.y);
-        }
-        if (io.flags & SWARM_STEP_CLIP_ACTIONS) {
-            // emulator_runner.py:113-118: rows with |a| >= MAX_MOVE_NORM(1) are divided by |a|, in place
-            if (io.flags & SWARM_STEP_ACTIONS_F64) {
-                const double d = sqrt(__dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y)));
-                if (d >= 1.0) {
-                    a.x = a.x / d; a.y = a.y / d;
-                    reinterpret_cast<double2*>(io.actions_f64)[(size_t)e * A + k] = a;
-                }
-            } else {
-                const float fx = (float)a.x, fy = (float)a.y;
-                const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
-                if (d >= 1.0f) {
-                    const float2 c = make_float2(__fdiv_rn(fx, d), __fdiv_rn(fy, d));
-                    reinterpret_cast<float2*>(io.actions_f32)[(size_t)e * A + k] = c;
-                    a = make_double2((double)c.x, (double)c.y);
-                }
-            }
-        }
-        sm.act[k] = a;
+    for (int k = g.tid; k < A; k += g.n) {
+        cp_async<16>(sg.as + k, ga + k);
+        cp_async<16>(sg.an + k, gna + k);
+        if (io.flags & SWARM_STEP_ACTIONS_F64)
+            cp_async<16>(sg.araw + 16 * k, reinterpret_cast<const double2*>(io.actions_f64) + (size_t)e * A + k);
+        else
+            cp_async<8>(sg.araw + 16 * k, reinterpret_cast<const float2*>(io.actions_f32) + (size_t)e * A + k);
     }
-    double2 nx[T];
-    {
-        const double2* gnx = reinterpret_cast<const double2*>(io.noise_x ? io.noise_x : st.noise_x) + (size_t)e * N;
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int j = threadIdx.x + t * blockDim.x;
-            nx[t] = j < N ? gnx[j] : make_double2(0.0, 0.0);
-        }
-    }
-    __syncthreads();
-
-    const double reward = env_step<MODE, PRECISE>(sm, kp, g, nx, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
-
-    // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
-    int elapsed = st.elapsed[e] + 1;
-    const bool done = (reward >= 0.0) || (kp.max_steps > 0 && elapsed >= kp.max_steps);
-    if (threadIdx.x == 0) {
-        io.reward[e] = (float)reward;
-        io.done[e] = done ? 1 : 0;
-    }
-    if (done && (io.flags & SWARM_STEP_AUTO_RESET)) {
-        // emulator_runner.py:127-132: the terminal reward/done are reported, the state (and
-        // therefore the observation) is the freshly reset episode's.  Block-uniform branch.
-        const uint32_t ep = st.episode[e];
-        env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
-        elapsed = 0;
-        if (threadIdx.x == 0) st.episode[e] = ep + 1;
-    }
-    if (threadIdx.x == 0) st.elapsed[e] = elapsed;
-
-    double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * N;
-    double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) ox[i] = sm.xs[i];
-    for (int k = threadIdx.x; k < A; k += blockDim.x) oa[k] = sm.as[k];
-
-    if (raster) env_raster(sm, sm.xs, sm.as, kp, g, grid_e, io.positions + (size_t)e * A * 2);
+    if (g.tid == g.n - 1) cp_async<4>(sg.misc, st.elapsed + e);
+    cp_async_commit();
 }
 
-// SwarmEnv._reset for the masked envs.
+// SwarmEnv._step + TimeLimit + SwarmRunner auto-reset + process_state for the whole batch.
+// Persistent CTAs (env e = blockIdx.x, += gridDim.x), two warp-specialised groups per CTA:
+//   threads [0, n_force)          FORCE group : prefetch the next env (cp.async), step, done /
+//                                               auto-reset, write the state back, hand the
+//                                               post-step positions over in sm.rx[it & 1]
+//   threads [n_force, blockDim.x) RASTER group: zero-fill the env's grid (before the positions even
+//                                               exist), wait for them, histogram + scatter
+// so that the rasteriser of env e (latency chains + 56 KB of stores) and the HBM reads of env
+// e + gridDim.x both run under a force phase.  Hand-over: named barriers FULL[b] (force arrives,
+// raster waits) and EMPTY[b] (raster arrives, force waits before re-using rx[b] two envs later).
 template <int MODE, bool PRECISE>
-__global__ void __launch_bounds__(512, 2) k_reset(const KP kp, const SwarmState st, const uint8_t* __restrict__ mask,
-                                               const SwarmInjectedDraws dr, const int has_draws) {
+__global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const SwarmStepIO io,
+                                       const SwarmInjectedDraws dr, const int has_draws, const int n_force) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = kp.N, A = kp.A;
+    const int n_all = blockDim.x, n_raster = n_all - n_force;
+    const bool raster = n_raster > 0;
+    Smem sm = carve(smem_raw, N, A, kp.G, 2, true, ModeT<MODE>::SYM);
+
+    if ((int)threadIdx.x < n_force) {
+        const Grp g = {(int)threadIdx.x, n_force};
+        if ((int)blockIdx.x < kp.E) prefetch_env(stage_at(smem_raw, N, A, 0), kp, st, io, blockIdx.x, g);
+        int it = 0;
+        for (int e = blockIdx.x; e < kp.E; e += gridDim.x, ++it) {
+            sm.st = stage_at(smem_raw, N, A, it & 1);
+            cp_async_wait_all();
+            g.sync();      // this env's stage buffer has landed; the other one is free again
+            if (e + (int)gridDim.x < kp.E)
+                prefetch_env(stage_at(smem_raw, N, A, (it + 1) & 1), kp, st, io, e + gridDim.x, g);
+
+            // actions: HBM dtype -> FP64, optional clip (the owner thread of agent k also moves it)
+            for (int k = g.tid; k < A; k += g.n) {
+                double2 a;
+                if (io.flags & SWARM_STEP_ACTIONS_F64) {
+                    a = *reinterpret_cast<const double2*>(sm.st.araw + 16 * k);
+                } else {
+                    const float2 f = *reinterpret_cast<const float2*>(sm.st.araw + 16 * k);
+                    a = make_double2((double)f.x, (double)f.y);
+                }
+                if (io.flags & SWARM_STEP_CLIP_ACTIONS) {
+                    // emulator_runner.py:113-118: rows with |a| >= MAX_MOVE_NORM(1) are divided by |a|, in place
+                    if (io.flags & SWARM_STEP_ACTIONS_F64) {
+                        const double d = sqrt(__dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y)));
+                        if (d >= 1.0) {
+                            a.x = a.x / d; a.y = a.y / d;
+                            reinterpret_cast<double2*>(io.actions_f64)[(size_t)e * A + k] = a;
+                        }
+                    } else {
+                        const float fx = (float)a.x, fy = (float)a.y;
+                        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));
+                        if (d >= 1.0f) {
+                            const float2 c = make_float2(__fdiv_rn(fx, d), __fdiv_rn(fy, d));
+                            reinterpret_cast<float2*>(io.actions_f32)[(size_t)e * A + k] = c;
+                            a = make_double2((double)c.x, (double)c.y);
+                        }
+                    }
+                }
+                sm.act[k] = a;
+            }
+
+            const double reward = env_step<MODE, PRECISE>(sm, kp, g, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
+
+            // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
+            int elapsed = sm.st.misc[0] + 1;
+            const bool done = (reward >= 0.0) || (kp.max_steps > 0 && elapsed >= kp.max_steps);
+            if (g.tid == 0) {
+                io.reward[e] = (float)reward;
+                io.done[e] = done ? 1 : 0;
+            }
+            if (done && (io.flags & SWARM_STEP_AUTO_RESET)) {
+                // emulator_runner.py:127-132: the terminal reward/done are reported, the state (and
+                // therefore the observation) is the freshly reset episode's.  Group-uniform branch.
+                const uint32_t ep = st.episode[e];
+                env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
+                elapsed = 0;
+                if (g.tid == 0) st.episode[e] = ep + 1;
+            }
+            if (g.tid == 0) st.elapsed[e] = elapsed;
+
+            if (raster && it >= 2) {   // wait until the raster group has let go of rx[it & 1] (two envs ago)
+                if (it & 1) bar_sync<BAR_EMPTY1>(n_all); else bar_sync<BAR_EMPTY0>(n_all);
+            }
+            double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * N;
+            double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
+            double2* rx = (it & 1) ? sm.rx[1] : sm.rx[0];
+            for (int i = g.tid; i < N; i += g.n) {
+                const double2 q = sm.st.xs[i];
+                ox[i] = q;
+                if (raster) rx[i] = q;
+            }
+            for (int k = g.tid; k < A; k += g.n) {
+                const double2 q = sm.st.as[k];
+                oa[k] = q;
+                if (raster) rx[N + k] = q;
+            }
+            if (raster) {
+                __threadfence_block();
+                if (it & 1) bar_arrive<BAR_FULL1>(n_all); else bar_arrive<BAR_FULL0>(n_all);
+            }
+        }
+    } else {
+        const RGrp g = {(int)threadIdx.x - n_force, n_raster};
+        const int cells = kp.G * kp.G;
+        raster_table_clear(sm, cells, g);
+        int it = 0;
+        for (int e = blockIdx.x; e < kp.E; e += gridDim.x, ++it) {
+            float* grid_e = io.grid + (size_t)e * cells * 2;
+            // The observation is ~99 % zeros: stream them out while the force group still computes;
+            // the non-zero cells are scattered over them afterwards.
+            raster_zero_fill(grid_e, cells, g.tid, g.n);
+            if (it & 1) bar_sync<BAR_FULL1>(n_all); else bar_sync<BAR_FULL0>(n_all);
+            env_raster(sm, (it & 1) ? sm.rx[1] : sm.rx[0], kp, g, grid_e, io.positions + (size_t)e * A * 2);
+            if (e + 2 * (int)gridDim.x < kp.E) {   // the force group will wait for this buffer again
+                if (it & 1) bar_arrive<BAR_EMPTY1>(n_all); else bar_arrive<BAR_EMPTY0>(n_all);
+            }
+        }
+    }
+}
+
+// SwarmEnv._reset for the masked envs (one CTA per env).
+template <int MODE, bool PRECISE>
+__global__ void __maxnreg__(64) k_reset(const KP kp, const SwarmState st, const uint8_t* __restrict__ mask,
+                                        const SwarmInjectedDraws dr, const int has_draws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, MODE == 1);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM);
     const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const uint32_t ep = st.episode[e];
     env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
     double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * kp.N;
     double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * kp.A;
-    for (int i = threadIdx.x; i < kp.N; i += blockDim.x) ox[i] = sm.xs[i];
-    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) oa[k] = sm.as[k];
-    if (threadIdx.x == 0) {
+    for (int i = g.tid; i < kp.N; i += g.n) ox[i] = sm.st.xs[i];
+    for (int k = g.tid; k < kp.A; k += g.n) oa[k] = sm.st.as[k];
+    if (g.tid == 0) {
         st.elapsed[e] = 0;
         st.episode[e] = ep + 1;
     }
 }
 
-// SwarmStateProcessor.process_state for the batch.
-template <int MODE>
-__global__ void __launch_bounds__(512, 2) k_rasterize(const KP kp, const double* __restrict__ x,
+// SwarmStateProcessor.process_state for the batch (standalone: one CTA per env).
+__global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __restrict__ x,
                                                    const double* __restrict__ xa, float* __restrict__ grid,
                                                    uint8_t* __restrict__ positions, double* __restrict__ box) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, MODE == 1);
-    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
-    float* grid_e = grid + (size_t)e * kp.G * kp.G * 2;
+    const int cells = kp.G * kp.G;
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 0, false, 0);
+    const RGrp g = {(int)threadIdx.x, (int)blockDim.x};
+    float* grid_e = grid + (size_t)e * cells * 2;
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
-    for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
-    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
-    raster_zero_fill(grid_e, kp.G * kp.G, g.tid, g.n);
-    __syncthreads();
-    env_raster(sm, sm.xs, sm.as, kp, g, grid_e, positions + (size_t)e * kp.A * 2);
-    if (box && threadIdx.x == 0) {       // sm.box[0] was published before env_raster's first barrier
+    double2* pts = sm.rx[0];
+    for (int i = g.tid; i < kp.N; i += g.n) pts[i] = gx[i];
+    for (int k = g.tid; k < kp.A; k += g.n) pts[kp.N + k] = ga[k];
+    raster_zero_fill(grid_e, cells, g.tid, g.n);
+    raster_table_clear(sm, cells, g);
+    g.sync();
+    env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2);
+    if (box && g.tid == 0) {
         const double m = sm.box[0];
         box[4 * e + 0] = m - kp.half_w;
         box[4 * e + 1] = m + kp.half_w;
@@ -149,33 +210,36 @@ __global__ void __launch_bounds__(512, 2) k_rasterize(const KP kp, const double*
     }
 }
 
-// SwarmEnv.v_calculate for the batch (no integration).
+// SwarmEnv.v_calculate for the batch (no integration; one CTA per env).
 template <int MODE, bool PRECISE>
-__global__ void __launch_bounds__(512, 2) k_forces(const KP kp, const double* __restrict__ x,
-                                                const double* __restrict__ xa, float* __restrict__ v,
-                                                float* __restrict__ reward) {
+__global__ void __maxnreg__(64) k_forces(const KP kp, const double* __restrict__ x,
+                                         const double* __restrict__ xa, float* __restrict__ v,
+                                         float* __restrict__ reward) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     constexpr int T = ModeT<MODE>::T;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, MODE == 1);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM);
+    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
-    for (int i = threadIdx.x; i < kp.N; i += blockDim.x) sm.xs[i] = gx[i];
-    for (int k = threadIdx.x; k < kp.A; k += blockDim.x) sm.as[k] = ga[k];
-    __syncthreads();
-    const Grp g = {(int)threadIdx.x, (int)blockDim.x};
-    stage_sources<MODE>(sm, kp, g);
-    __syncthreads();
+    for (int i = g.tid; i < kp.N; i += g.n) sm.st.xs[i] = gx[i];
+    float4* ag = agent_sources<MODE>(sm, kp);
+    for (int k = g.tid; k < kp.A; k += g.n) ag[k] = split_hilo(ga[k], kp.cscale);
+    stage_locusts<MODE>(sm, kp, g);
+    g.sync();
     float vx[T], vy[T];
-    const double r = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
+    const double en = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
+    energy_put(sm, g, en);
     if (v) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const int j = threadIdx.x + t * blockDim.x;
+            const int j = target_index<MODE>(g, t);
             if (j < kp.N) reinterpret_cast<float2*>(v)[(size_t)e * kp.N + j] = make_float2(vx[t], vy[t]);
         }
     }
-    if (reward && threadIdx.x == 0) reward[e] = (float)r;
+    g.sync();
+    const double r = energy_get(sm, kp, g);
+    if (reward && g.tid == 0) reward[e] = (float)r;
 }
 
 // SwarmRunner.get_local_states for the batch: (E,A,G,G,3) from (E,G,G,2) + (E,A,2).
@@ -263,13 +327,28 @@ int cuda_fail(cudaError_t err, const char* what) {
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kMaxLocusts = 2048;
 
-// MODE 1: unordered pairs, one thread per locust (N <= 512); MODE 2/4: ordered pairs, T targets per thread
-int force_mode(int N) { return N <= kSymMaxLocusts ? 1 : (N <= 1024 ? 2 : 4); }
+// N <= 512: unordered pairs -- MODE 3 (64-wide super-tiles, two targets per lane) when N pads to a
+// multiple of 64 anyway, else MODE 1 (32-wide tiles, one target per lane); N > 512: ordered pairs
+// with 2 or 4 targets per thread (MODE 2/4).
+int force_mode(int N) {
+    if (N <= kSymMaxLocusts) return ((N + 63) / 64) * 64 == ((N + 31) / 32) * 32 ? 3 : 1;
+    return N <= 1024 ? 2 : 4;
+}
+int force_sym(int mode) { return mode == 1 ? 1 : (mode == 3 ? 2 : 0); }
 
+// threads of the force group
 int block_threads(int N) {
-    const int T = force_mode(N);
-    const int per = (N + T - 1) / T;
+    const int mode = force_mode(N);
+    if (mode == 3) return ((N + 63) / 64) * 32;
+    const int per = (N + mode - 1) / mode;
     return ((per + 31) / 32) * 32;
+}
+
+// threads of the raster group riding along with the force group in k_step
+int raster_threads(int N, int A) { return (N + A) <= 128 ? 32 : 64; }
+
+size_t step_smem(const SwarmParams* p, bool raster, int n_stage = 2) {
+    return smem_bytes(p->n_locusts, p->n_agents, p->grid_size, n_stage, true, raster, force_sym(force_mode(p->n_locusts)));
 }
 
 int validate(const SwarmParams* p, int min_agents = 1) {
@@ -279,7 +358,7 @@ int validate(const SwarmParams* p, int min_agents = 1) {
     if (p->grid_size < 2 || p->grid_size > 255) return SWARM_ERR_SIZE;      // positions are uint8
     if (p->n_burn_in < 0 || p->max_episode_steps < 0) return SWARM_ERR_SIZE;
     if (p->math_mode != 0 && p->math_mode != 1) return SWARM_ERR_FLAGS;
-    if (smem_bytes(p->n_locusts, p->n_agents, p->grid_size, true, force_mode(p->n_locusts) == 1) > kMaxSmem) return SWARM_ERR_SIZE;
+    if (step_smem(p, true) > kMaxSmem) return SWARM_ERR_SIZE;
     if (p->env_id_offset < 0 || p->env_id_offset + p->n_envs > (int64_t)0xffffffffLL) return SWARM_ERR_SIZE;
     return SWARM_OK;
 }
@@ -300,12 +379,66 @@ KP make_kp(const SwarmParams* p) {
     return k;
 }
 
+// Per (device, kernel) launch cache: the opt-in shared-memory ceiling already granted and the
+// occupancy (CTAs/SM) of the configurations seen, so that the steady-state cost of an entry
+// point is one cudaGetDevice + one launch.
+struct KernelCache {
+    std::mutex mu;
+    std::map<std::pair<int, const void*>, size_t> smem_set;
+    std::map<std::tuple<int, const void*, int, size_t>, int> occupancy;
+    std::map<int, int> sms;
+};
+KernelCache& cache() {
+    static KernelCache c;
+    return c;
+}
+
+int current_device(int* dev) {
+    cudaError_t err = cudaGetDevice(dev);
+    return err == cudaSuccess ? SWARM_OK : cuda_fail(err, "cudaGetDevice");
+}
+
 template <typename K>
 int prep(K kernel, size_t smem) {
-    if (smem > 48 * 1024) {
+    if (smem <= 48 * 1024) return SWARM_OK;
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    KernelCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    size_t& have = c.smem_set[std::make_pair(dev, (const void*)kernel)];
+    if (smem > have) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute");
+        have = smem;
     }
+    return SWARM_OK;
+}
+
+// grid of a persistent kernel: every SM filled to its occupancy, never more CTAs than envs
+template <typename K>
+int persistent_grid(K kernel, int threads, size_t smem, int n_envs, int* grid) {
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    KernelCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto s = c.sms.find(dev);
+    if (s == c.sms.end()) {
+        int n = 0;
+        cudaError_t err = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceGetAttribute");
+        s = c.sms.emplace(dev, n).first;
+    }
+    const auto key = std::make_tuple(dev, (const void*)kernel, threads, smem);
+    auto o = c.occupancy.find(key);
+    if (o == c.occupancy.end()) {
+        int per_sm = 0;
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        if (err != cudaSuccess) return cuda_fail(err, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (per_sm < 1) per_sm = 1;
+        o = c.occupancy.emplace(key, per_sm).first;
+    }
+    const long long slots = (long long)s->second * o->second;
+    *grid = (int)(n_envs < slots ? n_envs : slots);
     return SWARM_OK;
 }
 
@@ -318,9 +451,9 @@ int check_launch(const char* what) {
     switch (T_) {                        \
         case 1: { constexpr int TT = 1; __VA_ARGS__; } break; \
         case 2: { constexpr int TT = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int TT = 3; __VA_ARGS__; } break; \
         default: { constexpr int TT = 4; __VA_ARGS__; } break; \
     }
-#define SMEM(kp_, raster_) smem_bytes((kp_).N, (kp_).A, (kp_).G, (raster_), force_mode((kp_).N) == 1)
 
 const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -358,7 +491,7 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
     if (!st || !st->x || !st->xa || !st->noise_x || !st->noise_a || !st->elapsed || !st->episode) return SWARM_ERR_NULL;
     if (draws && !draws_complete(draws)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = SMEM(kp, false);
+    const size_t smem = step_smem(p, false, 1);
     const int nt = block_threads(kp.N);
     cudaStream_t s = (cudaStream_t)stream;
     DISPATCH_T(force_mode(kp.N),
@@ -384,16 +517,23 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
     if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = SMEM(kp, io->grid != nullptr);
-    const int nt = block_threads(kp.N);
+    const bool raster = io->grid != nullptr;
+    const size_t smem = step_smem(p, raster);
+    const int nf = block_threads(kp.N);
+    const int nt = nf + (raster ? raster_threads(kp.N, kp.A) : 0);
+    const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;
+    const int has = reset_draws ? 1 : 0;
+    int grid = 0;
     cudaStream_t s = (cudaStream_t)stream;
     DISPATCH_T(force_mode(kp.N),
         if (p->math_mode) {
             if ((rc = prep(k_step<TT, true>, smem))) return rc;
-            k_step<TT, true><<<kp.E, nt, smem, s>>>(kp, *st, *io, reset_draws ? *reset_draws : kNoDraws, reset_draws ? 1 : 0);
+            if ((rc = persistent_grid(k_step<TT, true>, nt, smem, kp.E, &grid))) return rc;
+            k_step<TT, true><<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
         } else {
             if ((rc = prep(k_step<TT, false>, smem))) return rc;
-            k_step<TT, false><<<kp.E, nt, smem, s>>>(kp, *st, *io, reset_draws ? *reset_draws : kNoDraws, reset_draws ? 1 : 0);
+            if ((rc = persistent_grid(k_step<TT, false>, nt, smem, kp.E, &grid))) return rc;
+            k_step<TT, false><<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
         })
     return check_launch("swarm_step");
 }
@@ -424,12 +564,10 @@ int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa, flo
     if (!x || !grid) return SWARM_ERR_NULL;
     if (p->n_agents > 0 && (!xa || !positions)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = SMEM(kp, true);
-    const int nt = block_threads(kp.N);
-    cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(force_mode(kp.N),
-        if ((rc = prep(k_rasterize<TT>, smem))) return rc;
-        k_rasterize<TT><<<kp.E, nt, smem, s>>>(kp, x, xa, grid, positions, box);)
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, true, 0);
+    const int nt = (kp.N + kp.A) <= 128 ? 64 : 128;
+    if ((rc = prep(k_rasterize, smem))) return rc;
+    k_rasterize<<<kp.E, nt, smem, (cudaStream_t)stream>>>(kp, x, xa, grid, positions, box);
     return check_launch("swarm_rasterize");
 }
 
@@ -463,7 +601,7 @@ int swarm_forces(const SwarmParams* p, const double* x, const double* xa, float*
     if (rc) return rc;
     if (!x || !xa || (!v && !reward)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = SMEM(kp, false);
+    const size_t smem = step_smem(p, false, 1);
     const int nt = block_threads(kp.N);
     cudaStream_t s = (cudaStream_t)stream;
     DISPATCH_T(force_mode(kp.N),

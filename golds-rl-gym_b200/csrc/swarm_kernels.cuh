@@ -1,6 +1,11 @@
-// Block-level device code of the swarm hot path (sm_100a).  One CTA owns one env:
-//   * the env's FP64 integrator state lives in shared memory for the whole kernel
-//     (step, auto-reset burn-in and rasterise never round-trip through HBM);
+// Block-level device code of the swarm hot path (sm_100a).  A CTA works on one env at a time
+// with two warp-specialised thread groups: the FORCE group (dynamics, reward, auto-reset) and
+// the RASTER group (occupancy grid of the env the force group finished last), so that the
+// rasteriser's latency chains and HBM stores run under the next env's force phase:
+//   * an env's FP64 integrator state, its frozen noise row and its actions are prefetched
+//     (cp.async) into one of two shared-memory STAGE buffers while the previous env is being
+//     stepped, and stay there for the whole step (step, auto-reset burn-in and rasterise
+//     never round-trip through HBM);
 //   * the O(N^2) pair forces run in FP32 on an FP32 hi/lo split of the positions staged in
 //     shared memory.  For N <= 512 every UNORDERED pair is evaluated once (the pair force is
 //     exactly antisymmetric): a warp owns a 32-locust tile, walks the other tiles with a
@@ -10,8 +15,12 @@
 //     T targets per thread in registers and broadcast LDS.128 sources;
 //   * reward is a warp-shuffle + shared-memory reduction in FP64;
 //   * the occupancy grid is a shared-memory-privatised histogram with warp-aggregated
-//     atomics (match.any), written out as a streaming zero fill + sparse scatter.  Its
-//     counter table aliases the force scratch (the two phases never overlap).
+//     atomics (match.any), written out as a streaming zero fill + sparse scatter; the
+//     counter table is cleaned cell by cell by the threads that scatter, never re-cleared.
+//
+// Everything here is __forceinline__ on purpose: the shared-memory pointers of `Smem` must
+// stay in registers with a known address space (a spilled pointer turns every LDS/STS into
+// a generic LD/ST).
 //
 // Reference semantics restated here: fed_gym/envs/multiagent.py:30-115,
 // fed_gym/agents/state_processors.py:25-42.
@@ -38,18 +47,29 @@ struct KP {
     uint32_t env_off;
 };
 
+// One STAGE buffer = everything the step of one env reads from HBM:
+//   x (N) | noise_x (N) | xa (A) | noise_a (A) | raw actions (A x 16 B) | misc (16 B: elapsed)
+struct Stage {
+    double2* xs;            // N   locust positions (FP64 integrator state, updated in place)
+    double2* nx;            // N   locust noise row of the current step (unscaled)
+    double2* as;            // A   agent positions
+    double2* an;            // A   agent noise row
+    unsigned char* araw;    // A x 16 B: the env's actions as they sit in HBM (f32 pair or f64 pair)
+    int* misc;              // [0] = TimeLimit elapsed steps
+};
+
 struct Smem {
-    double2* xs;      // N   locust positions (FP64 integrator state)
-    double2* as;      // A   agent positions
-    double2* act;     // A   current actions
-    double2* an;      // A   current agent noise row (unscaled)
+    Stage st;         // the stage buffer of the env being stepped
+    double2* act;     // A   actions after conversion / clipping
     double* red;      // 32  reduction scratch
     double* box;      // 2   rasteriser: mean x
-    // ---- scratch, aliased between the force phase and the rasteriser
+    // ---- force scratch
     float4* src;      // FP32 sources (hi_x, hi_y, lo_x, lo_y), x = hi + lo to ~2^-48.
-                      //   MODE 1: nt tiles x 64 (each 32-tile stored twice: wrap-free lane+k reads) + A agents
+                      //   MODE 1/3: nt 32-tiles x 64 (each tile stored twice: wrap-free lane+k reads) + A agents
                       //   MODE 2/4: N locusts + A agents
-    float2* slot;     // MODE 1: nt x (1 + nt/2) x 32 reaction-force partial sums
+    float2* slot;     // MODE 1/3: nt x nslots x 32 reaction-force partial sums
+    // ---- rasteriser (present when the kernel rasterises)
+    double2* rx[2];   // 2 x (N+A): post-step positions handed from the force to the raster group
     uint32_t* table;  // G*G packed cell counters: lo16 locusts, hi16 agents
     int* cid;         // N+A: cell written out by this point (or -1)
 };
@@ -57,38 +77,71 @@ struct Smem {
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
 __host__ __device__ inline int n_tiles(int N) { return (N + 31) >> 5; }
 
-__host__ __device__ inline size_t smem_src_bytes(int N, int A, bool sym) {
-    return smem_align(sizeof(float4) * (sym ? (size_t)n_tiles(N) * 64 + A : (size_t)N + A));
+__host__ __device__ inline size_t smem_stage_bytes(int N, int A) { return 16 * ((size_t)2 * N + 3 * A + 1); }
+__host__ __device__ inline int sym_tiles(int N, int sym);
+__host__ __device__ inline size_t smem_src_bytes(int N, int A, int sym) {
+    return smem_align(sizeof(float4) * (sym ? (size_t)sym_tiles(N, sym) * 64 + A : (size_t)N + A));
 }
-__host__ __device__ inline size_t smem_fixed_bytes(int N, int A) {
-    return smem_align(sizeof(double2) * N) + 3 * smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) +
-           smem_align(sizeof(double) * 2);
+__host__ __device__ inline size_t smem_fixed_bytes(int A) {
+    return smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) + smem_align(sizeof(double) * 2);
+}
+// sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3)
+__host__ __device__ inline int sym_tiles(int N, int sym) { return sym == 2 ? 2 * ((N + 63) >> 6) : n_tiles(N); }
+__host__ __device__ inline int sym_slots(int N, int sym) {
+    return sym == 2 ? 1 + ((N + 63) >> 6) / 2 : 1 + n_tiles(N) / 2;
+}
+__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym) {
+    return smem_src_bytes(N, A, sym) +
+           (sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * sym_slots(N, sym) * 32) : 0);
 }
 __host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G) {
-    return smem_align(sizeof(uint32_t) * G * G) + smem_align(sizeof(int) * (N + A));
+    return 2 * smem_align(sizeof(double2) * (N + A)) + smem_align(sizeof(uint32_t) * G * G) +
+           smem_align(sizeof(int) * (N + A));
 }
-__host__ __device__ inline size_t smem_bytes(int N, int A, int G, bool raster, bool sym) {
-    const int nt = n_tiles(N);
-    size_t force = smem_src_bytes(N, A, sym) + (sym ? smem_align(sizeof(float2) * nt * (1 + nt / 2) * 32) : 0);
-    size_t rast = raster ? smem_raster_bytes(N, A, G) : 0;
-    return smem_fixed_bytes(N, A) + (force > rast ? force : rast);
+// n_stage: stage buffers (2 in the pipelined step kernel, 1 in reset/forces, 0 in the rasteriser)
+__host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, bool raster, int sym) {
+    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(A) + (force ? smem_force_bytes(N, A, sym) : 0) +
+           (raster ? smem_raster_bytes(N, A, G) : 0);
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, bool sym) {
+__device__ __forceinline__ Stage stage_at(unsigned char* base, int N, int A, int b) {
+    unsigned char* p = base + (size_t)b * smem_stage_bytes(N, A);
+    Stage s;
+    s.xs = reinterpret_cast<double2*>(p);
+    s.nx = s.xs + N;
+    s.as = s.nx + N;
+    s.an = s.as + A;
+    s.araw = reinterpret_cast<unsigned char*>(s.an + A);
+    s.misc = reinterpret_cast<int*>(s.araw + 16 * (size_t)A);
+    return s;
+}
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, int n_stage, bool force, int sym) {
     Smem s;
-    size_t o = 0;
-    s.xs = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * N);
-    s.as = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
+    s.st = stage_at(base, N, A, 0);
+    size_t o = (size_t)n_stage * smem_stage_bytes(N, A);
     s.act = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * A);
-    s.an = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * A);
     s.red = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 32);
     s.box = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 2);
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
-    s.table = reinterpret_cast<uint32_t*>(base + o);
-    s.cid = reinterpret_cast<int*>(base + o + smem_align(sizeof(uint32_t) * G * G));
+    if (force) o += smem_force_bytes(N, A, sym);
+    s.rx[0] = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * (N + A));
+    s.rx[1] = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * (N + A));
+    s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_align(sizeof(uint32_t) * G * G);
+    s.cid = reinterpret_cast<int*>(base + o);
     return s;
 }
+
+// ------------------------------------------------------------------------------------------
+// cp.async (LDGSTS): HBM -> shared memory without staging through registers
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // multiagent.py:70-86  x_update = cutoff; x += dt*v + noise; cutoff   (FP64, no FMA contraction
@@ -104,12 +157,23 @@ __device__ __forceinline__ void move_particle(double2& p, double2 v, double2 n, 
     if (p.y <= 0.0) p.y = 0.0;
 }
 
-// The threads that cooperate on one env (today: the whole CTA).
-struct Grp {
-    int tid;   // thread index inside the group
-    int n;     // threads in the group (multiple of 32)
-    __device__ __forceinline__ void sync() const { __syncthreads(); }
+// Named barriers (bar.sync id, n) of the warp-specialised step kernel.  0 stays __syncthreads.
+enum : int { BAR_FORCE = 1, BAR_RASTER = 2, BAR_FULL0 = 3, BAR_FULL1 = 4, BAR_EMPTY0 = 5, BAR_EMPTY1 = 6 };
+
+template <int ID>
+__device__ __forceinline__ void bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_arrive(int n) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+
+// A group of whole warps that cooperates on one env: tid in [0,n), n a multiple of 32.
+template <int BAR>
+struct GrpT {
+    int tid;
+    int n;
+    __device__ __forceinline__ void sync() const { bar_sync<BAR>(n); }
 };
+typedef GrpT<BAR_FORCE> Grp;     // dynamics
+typedef GrpT<BAR_RASTER> RGrp;   // rasteriser
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -161,24 +225,43 @@ __device__ __forceinline__ float4 split_hilo(const double2 p, const double c) {
     return make_float4(hx, hy, (float)(sx - (double)hx), (float)(sy - (double)hy));
 }
 
-// Stage the scaled FP32 hi/lo sources: locusts then agents.
+// MODE: 1 = unordered pairs, a warp owns a 32-locust tile, 1 target per lane
+//       3 = unordered pairs, a warp owns a 64-locust super-tile, 2 targets per lane (half the
+//           shared-memory loads and shuffles per pair; used when N pads to 64 as well as to 32)
+//       2/4 = ordered pairs, 2/4 targets per thread (N > 512)
 template <int MODE>
-__device__ __forceinline__ void stage_sources(const Smem& sm, const KP& kp, const Grp& g) {
-    const int N = kp.N, A = kp.A;
-    if (MODE == 1) {
-        const int nt = n_tiles(N);
+struct ModeT {
+    static constexpr int T = MODE == 1 ? 1 : (MODE == 3 ? 2 : MODE);
+    static constexpr int SYM = MODE == 1 ? 1 : (MODE == 3 ? 2 : 0);
+};
+
+// locust owned by thread g.tid as its t-th target
+template <int MODE>
+__device__ __forceinline__ int target_index(const Grp& g, int t) {
+    return MODE == 3 ? ((g.tid >> 5) * 64 + t * 32 + (g.tid & 31)) : g.tid + t * g.n;
+}
+
+template <int MODE>
+__device__ __forceinline__ float4* agent_sources(const Smem& sm, const KP& kp) {
+    return sm.src + (ModeT<MODE>::SYM ? sym_tiles(kp.N, ModeT<MODE>::SYM) * 64 : kp.N);
+}
+
+// Stage the scaled FP32 hi/lo sources of the locusts.  Thread j stages element j.
+template <int MODE>
+__device__ __forceinline__ void stage_locusts(const Smem& sm, const KP& kp, const Grp& g) {
+    const int N = kp.N;
+    if (ModeT<MODE>::SYM) {
+        const int nt = sym_tiles(N, ModeT<MODE>::SYM);
         // pad lanes sit far away: as sources they contribute exactly 0 (both exponentials underflow)
         const float4 pad = make_float4(1e15f, 0.f, 0.f, 0.f);
         for (int j = g.tid; j < nt * 32; j += g.n) {
-            const float4 q = j < N ? split_hilo(sm.xs[j], kp.cscale) : pad;
+            const float4 q = j < N ? split_hilo(sm.st.xs[j], kp.cscale) : pad;
             float4* t = sm.src + (j >> 5) * 64 + (j & 31);
             t[0] = q;
             t[32] = q;
         }
-        for (int k = g.tid; k < A; k += g.n) sm.src[nt * 64 + k] = split_hilo(sm.as[k], kp.cscale);
     } else {
-        for (int i = g.tid; i < N; i += g.n) sm.src[i] = split_hilo(sm.xs[i], kp.cscale);
-        for (int k = g.tid; k < A; k += g.n) sm.src[N + k] = split_hilo(sm.as[k], kp.cscale);
+        for (int i = g.tid; i < N; i += g.n) sm.src[i] = split_hilo(sm.st.xs[i], kp.cscale);
     }
 }
 
@@ -191,7 +274,7 @@ __device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const fl
                                          float& ax, float& ay, float& bx, float& by) {
     bx = 0.f;
     by = 0.f;
-#pragma unroll
+#pragma unroll 8
     for (int k = K0; k <= K1; ++k) {
         const float4 q = tl[k];
         const float dx = (q.x - tg.x) + (q.z - tg.z);
@@ -208,10 +291,11 @@ __device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const fl
     }
 }
 
-// MODE 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I meets
-// tiles I+1..I+floor((nt-1)/2) fully, tile I+nt/2 (nt even) half each way, and itself.
+// MODE 1, part 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I
+// meets tiles I+1..I+floor((nt-1)/2) fully, tile I+nt/2 (nt even) half each way, and itself.
+// The reaction sums land in sm.slot; the caller must barrier before forces_sym_finish.
 template <bool PRECISE>
-__device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
+__device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
     const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
     const int nxt = (lane + 1) & 31;
@@ -239,17 +323,135 @@ __device__ __forceinline__ void forces_sym(const Smem& sm, const KP& kp, const G
         tile_sym<0, 15, PRECISE>(S + B * 64 + lane + koff, tg, kp, nxt, ax, ay, bx, by);
         sm.slot[(B * nslots + o) * 32 + ((lane + 15 + koff) & 31)] = make_float2(bx, by);
     }
-    g.sync();
-    for (int o = 0; o < nslots; ++o) {          // fixed order: bitwise reproducible
+}
+
+// MODE 1, part 2: add the reactions (fixed order: bitwise reproducible) and the agents' pull.
+template <bool PRECISE>
+__device__ __forceinline__ void forces_sym_finish(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
+    const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
+    for (int o = 0; o < nslots; ++o) {
         const float2 r = sm.slot[(I * nslots + o) * 32 + lane];
         ax += r.x;
         ay += r.y;
     }
-    const float4* ag = S + nt * 64;             // agents act on locusts only (multiagent.py:108-113)
+    const float4 tg = sm.src[I * 64 + lane];
+    const float4* ag = sm.src + nt * 64;        // agents act on locusts only (multiagent.py:108-113)
     for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, ax, ay);
 }
 
-// MODE 2/4: ordered pairs, T targets per thread (j = tid + t*blockDim.x), broadcast LDS.128 sources.
+// ---- MODE 3: 64-wide super-tiles, two targets (A: first half, B: second half) per lane -------
+template <bool REACT, bool PRECISE>
+__device__ __forceinline__ void pair_sym(const float4 q, const float4 tg, const KP& kp, float& ax, float& ay,
+                                         float& bx, float& by) {
+    const float dx = (q.x - tg.x) + (q.z - tg.z);
+    const float dy = (q.y - tg.y) + (q.w - tg.w);
+    const float w = pair_weight<PRECISE>(dx, dy, kp);
+    ax = fmaf(w, dx, ax);
+    ay = fmaf(w, dy, ay);
+    if (REACT) {
+        bx = fmaf(-w, dx, bx);
+        by = fmaf(-w, dy, by);
+    }
+}
+
+// Rotation steps K0..K1 against one doubled half-tile tl (= S + H*64 + lane): in step k the lane
+// meets element (lane+k)%32 and evaluates it against its A and/or B target; (bx,by) is the
+// reaction on the met element and moves one lane down per step.  CONT: (bx,by) continues from an
+// earlier call (shuffle before the first step too).  On return lane l holds element (l+K1)%32's.
+template <int K0, int K1, bool DO_A, bool DO_B, bool REACT_A, bool REACT_B, bool CONT, bool PRECISE>
+__device__ __forceinline__ void tile2(const float4* __restrict__ tl, const float4 tgA, const float4 tgB, const KP& kp,
+                                      const int nxt, float& aAx, float& aAy, float& aBx, float& aBy, float& bx,
+                                      float& by) {
+#pragma unroll 8
+    for (int k = K0; k <= K1; ++k) {
+        if ((REACT_A || REACT_B) && (CONT || k > K0)) {
+            bx = __shfl_sync(kFull, bx, nxt);
+            by = __shfl_sync(kFull, by, nxt);
+        }
+        const float4 q = tl[k];
+        if (DO_A) pair_sym<REACT_A, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
+        if (DO_B) pair_sym<REACT_B, PRECISE>(q, tgB, kp, aBx, aBy, bx, by);
+    }
+}
+
+// MODE 3, part 1.  Warp I owns super-tile I = half-tiles 2I (A targets) and 2I+1 (B targets).
+//   own super-tile: A x A and B x B by offsets 1..15 both ways + 16 one way; A x B split by offset:
+//                   (B target, A source) for offsets 0..15, (A target, B source) for 1..16;
+//   super-tiles I+1 .. I+floor((nt2-1)/2): all 64 x 64 pairs;  I+nt2/2 (nt2 even): half each way.
+template <bool PRECISE>
+__device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
+                                                   float (&vy)[2]) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
+    const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
+    const int nxt = (lane + 1) & 31;
+    const float4* S = sm.src;
+    const float4* tlA = S + (2 * I) * 64 + lane;
+    const float4* tlB = tlA + 64;
+    const float4 tgA = tlA[0], tgB = tlB[0];
+    float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f, bx = 0.f, by = 0.f;
+    // sources = own A half
+    tile2<0, 0, false, true, false, true, false, PRECISE>(tlA, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+    tile2<1, 15, true, true, true, true, true, PRECISE>(tlA, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+    sm.slot[((2 * I) * nslots) * 32 + ((lane + 15) & 31)] = make_float2(bx, by);
+    tile2<16, 16, true, false, false, false, false, PRECISE>(tlA, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+    // sources = own B half
+    bx = 0.f; by = 0.f;
+    tile2<1, 15, true, true, true, true, false, PRECISE>(tlB, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+    tile2<16, 16, true, true, true, false, true, PRECISE>(tlB, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+    sm.slot[((2 * I + 1) * nslots) * 32 + ((lane + 16) & 31)] = make_float2(bx, by);
+    const int nfull = (nt2 - 1) >> 1;
+    for (int o = 1; o <= nfull; ++o) {
+        int J = I + o;
+        if (J >= nt2) J -= nt2;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int H = 2 * J + h;
+            bx = 0.f; by = 0.f;
+            tile2<0, 31, true, true, true, true, false, PRECISE>(S + H * 64 + lane, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy,
+                                                                 bx, by);
+            sm.slot[(H * nslots + o) * 32 + ((lane + 31) & 31)] = make_float2(bx, by);
+        }
+    }
+    if ((nt2 & 1) == 0) {
+        // lane offsets 0..15 from the lower super-tile, 16..31 (= 1..16 seen from the partner) from the upper
+        const int o = nt2 >> 1;
+        const int J = I < o ? I + o : I - o;
+        const int koff = I < o ? 0 : 1;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int H = 2 * J + h;
+            bx = 0.f; by = 0.f;
+            tile2<0, 15, true, true, true, true, false, PRECISE>(S + H * 64 + lane + koff, tgA, tgB, kp, nxt, aAx, aAy, aBx,
+                                                                 aBy, bx, by);
+            sm.slot[(H * nslots + o) * 32 + ((lane + 15 + koff) & 31)] = make_float2(bx, by);
+        }
+    }
+    vx[0] = aAx; vy[0] = aAy; vx[1] = aBx; vy[1] = aBy;
+}
+
+// MODE 3, part 2: reactions (fixed order: bitwise reproducible) and the agents' pull.
+template <bool PRECISE>
+__device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
+                                                    float (&vy)[2]) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
+    const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
+    for (int o = 0; o < nslots; ++o) {
+        const float2 ra = sm.slot[((2 * I) * nslots + o) * 32 + lane];
+        const float2 rb = sm.slot[((2 * I + 1) * nslots + o) * 32 + lane];
+        vx[0] += ra.x; vy[0] += ra.y;
+        vx[1] += rb.x; vy[1] += rb.y;
+    }
+    const float4 tgA = sm.src[(2 * I) * 64 + lane], tgB = sm.src[(2 * I + 1) * 64 + lane];
+    const float4* ag = sm.src + nt2 * 128;      // agents act on locusts only (multiagent.py:108-113)
+    for (int k = 0; k < kp.A; ++k) {
+        const float4 q = ag[k];
+        pair_ordered<PRECISE>(q, tgA, kp, vx[0], vy[0]);
+        pair_ordered<PRECISE>(q, tgB, kp, vx[1], vy[1]);
+    }
+}
+
+// MODE 2/4: ordered pairs, T targets per thread (j = tid + t*n), broadcast LDS.128 sources.
 template <int T, bool PRECISE>
 __device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[T], float (&vy)[T]) {
     const int N = kp.N, S = kp.N + kp.A;
@@ -269,116 +471,123 @@ __device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, con
     }
 }
 
-template <int MODE>
-struct ModeT { static constexpr int T = MODE == 1 ? 1 : MODE; };
-
-// Forces on this thread's targets + block-wide reward = -mean_j |v_j|^2 (pre-cutoff v, wind and
-// gravity added).  Needs the staged sources visible; ends after a barrier.
+// SwarmEnv.v_calculate (multiagent.py:88-115) on staged sources: v of this thread's targets (wind
+// and gravity added, before any cutoff) and its share of sum_j |v_j|^2.  Needs the staged sources
+// visible (a barrier since stage_*); contains one group barrier in MODE 1.
 template <int MODE, bool PRECISE>
 __device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, const Grp& g,
                                               float (&vx)[ModeT<MODE>::T], float (&vy)[ModeT<MODE>::T]) {
     constexpr int T = ModeT<MODE>::T;
-    if (MODE == 1) forces_sym<PRECISE>(sm, kp, g, vx[0], vy[0]);
-    else forces_ordered<T, PRECISE>(sm, kp, g, vx, vy);
+    if constexpr (MODE == 1) {
+        forces_sym_tiles<PRECISE>(sm, kp, g, vx[0], vy[0]);
+        g.sync();
+        forces_sym_finish<PRECISE>(sm, kp, g, vx[0], vy[0]);
+    } else if constexpr (MODE == 3) {
+        forces_sym64_tiles<PRECISE>(sm, kp, g, vx, vy);
+        g.sync();
+        forces_sym64_finish<PRECISE>(sm, kp, g, vx, vy);
+    } else {
+        forces_ordered<T, PRECISE>(sm, kp, g, vx, vy);
+    }
     double e = 0.0;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         vx[t] += kp.U;
         vy[t] += kp.Gv;
-        if (g.tid + t * g.n < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
+        if (target_index<MODE>(g, t) < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
     }
+    return e;
+}
+
+// reward = -mean_j |v_j|^2 from the per-thread shares: warp shuffle, then one slot per warp.  The
+// caller barriers between energy_put and energy_get.
+__device__ __forceinline__ void energy_put(const Smem& sm, const Grp& g, double e) {
     e = warp_sum(e);
     if ((g.tid & 31) == 0) sm.red[g.tid >> 5] = e;
-    g.sync();
+}
+__device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const Grp& g) {
     double tot = 0.0;
     const int nw = g.n >> 5;
     for (int w = 0; w < nw; ++w) tot += sm.red[w];   // same order in every thread
     return -tot / (double)kp.N;
 }
 
-// SwarmEnv._step on the shared-memory state.  Preconditions: sm.xs/as/act/an filled and
-// visible (a __syncthreads since their last write); nx[t] = unscaled noise of own target t.
-// Postcondition: state updated and visible to the whole block; force scratch free again.
+// SwarmEnv._step on the stage buffer sm.st.  Preconditions: st.xs/nx/as/an and sm.act filled, each
+// element written by the thread that owns it here (element i <-> thread i mod n) or visible through
+// a barrier.  Postcondition: state updated and visible to the whole group; returns the reward.
 template <int MODE, bool PRECISE>
-__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const Grp& g,
-                                           const double2 (&nx)[ModeT<MODE>::T], float* v_out) {
+__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const Grp& g, float* v_out) {
     constexpr int T = ModeT<MODE>::T;
-    // multiagent.py:33-38  agents move first: v_action (+wind on x) through x_update
+    // multiagent.py:33-38  agents move first: v_action (+wind on x) through x_update; the mover
+    // stages the agent's NEW position as a force source (multiagent.py:39: old x, new xa)
+    float4* ag = agent_sources<MODE>(sm, kp);
     for (int k = g.tid; k < kp.A; k += g.n) {
-        double2 a = sm.as[k];
+        double2 a = sm.st.as[k];
         double2 w = sm.act[k];
         w.x = __dadd_rn(w.x, kp.wind);
-        move_particle(a, w, sm.an[k], kp.dt, kp.sigma);
-        sm.as[k] = a;
+        move_particle(a, w, sm.st.an[k], kp.dt, kp.sigma);
+        sm.st.as[k] = a;
+        ag[k] = split_hilo(a, kp.cscale);
     }
-    g.sync();
-    stage_sources<MODE>(sm, kp, g);      // old x, NEW xa (multiagent.py:39)
+    stage_locusts<MODE>(sm, kp, g);
     g.sync();
     float vx[T], vy[T];
-    const double reward = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
+    const double e = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
+    energy_put(sm, g, e);
     // multiagent.py:40  locusts move with the pre-cutoff v just computed
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const int j = g.tid + t * g.n;
+        const int j = target_index<MODE>(g, t);
         if (j < kp.N) {
             if (v_out) reinterpret_cast<float2*>(v_out)[j] = make_float2(vx[t], vy[t]);
-            double2 p = sm.xs[j];
-            move_particle(p, make_double2((double)vx[t], (double)vy[t]), nx[t], kp.dt, kp.sigma);
-            sm.xs[j] = p;
+            double2 p = sm.st.xs[j];
+            move_particle(p, make_double2((double)vx[t], (double)vy[t]), sm.st.nx[j], kp.dt, kp.sigma);
+            sm.st.xs[j] = p;
         }
     }
     g.sync();
-    return reward;
+    return energy_get(sm, kp, g);
 }
 
-// SwarmEnv._reset (multiagent.py:46-63) for env e: draws (injected or Philox), n_burn burn-in
-// steps with noise row k, then the frozen row n_burn is stored for all later steps (Q1).
+// SwarmEnv._reset (multiagent.py:46-63) for env e on the stage buffer: draws (injected or Philox),
+// n_burn burn-in steps with noise row k, then the frozen row n_burn is stored for all later
+// steps (Q1).  Ends with the state visible to the whole group.
 template <int MODE, bool PRECISE>
-__device__ __noinline__ void env_reset(const Smem& sm, const KP& kp, const Grp& g, int e, uint32_t episode,
-                                       const bool inj, const SwarmInjectedDraws& dr, const SwarmState& st) {
-    constexpr int T = ModeT<MODE>::T;
+__device__ __forceinline__ void env_reset(const Smem& sm, const KP& kp, const Grp& g, int e, uint32_t episode,
+                                          const bool inj, const SwarmInjectedDraws& dr, const SwarmState& st) {
     const int N = kp.N, A = kp.A;
     DrawCtx ctx;
     ctx.key = kp.key;
     ctx.env = kp.env_off + (uint32_t)e;
     ctx.episode = episode;
+    g.sync();      // the previous step's readers of red / src are done
     for (int i = g.tid; i < N; i += g.n)
-        sm.xs[i] = inj ? reinterpret_cast<const double2*>(dr.x0)[(size_t)e * N + i]
-                       : draw_uniform2(ctx, STREAM_X0, i);
+        sm.st.xs[i] = inj ? reinterpret_cast<const double2*>(dr.x0)[(size_t)e * N + i]
+                          : draw_uniform2(ctx, STREAM_X0, i);
     for (int k = g.tid; k < A; k += g.n)
-        sm.as[k] = inj ? reinterpret_cast<const double2*>(dr.xa0)[(size_t)e * A + k]
-                       : draw_uniform2(ctx, STREAM_XA0, k);
+        sm.st.as[k] = inj ? reinterpret_cast<const double2*>(dr.xa0)[(size_t)e * A + k]
+                          : draw_uniform2(ctx, STREAM_XA0, k);
     const int rows = kp.n_burn + 1;
     for (int r = 0; r <= kp.n_burn; ++r) {
-        double2 nx[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int j = g.tid + t * g.n;
-            nx[t] = make_double2(0.0, 0.0);
-            if (j < N)
-                nx[t] = inj ? reinterpret_cast<const double2*>(dr.particle_noise)[((size_t)e * rows + r) * N + j]
-                            : draw_normal2(ctx, STREAM_NOISE_X, r, j);
-        }
-        if (r == kp.n_burn) {   // frozen row: kept in HBM for every later step
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const int j = g.tid + t * g.n;
-                if (j < N) reinterpret_cast<double2*>(st.noise_x)[(size_t)e * N + j] = nx[t];
-            }
-            for (int k = g.tid; k < A; k += g.n)
-                reinterpret_cast<double2*>(st.noise_a)[(size_t)e * A + k] =
-                    inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
-                        : draw_normal2(ctx, STREAM_NOISE_A, r, k);
-            break;
+        for (int j = g.tid; j < N; j += g.n) {
+            const double2 z = inj ? reinterpret_cast<const double2*>(dr.particle_noise)[((size_t)e * rows + r) * N + j]
+                                  : draw_normal2(ctx, STREAM_NOISE_X, r, j);
+            sm.st.nx[j] = z;
+            if (r == kp.n_burn) reinterpret_cast<double2*>(st.noise_x)[(size_t)e * N + j] = z;   // frozen row -> HBM
         }
         for (int k = g.tid; k < A; k += g.n) {
-            sm.act[k] = inj ? reinterpret_cast<const double2*>(dr.burn_actions)[((size_t)e * kp.n_burn + r) * A + k]
-                            : draw_normal2(ctx, STREAM_BURN, r, k);
-            sm.an[k] = inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
-                           : draw_normal2(ctx, STREAM_NOISE_A, r, k);
+            const double2 z = inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
+                                  : draw_normal2(ctx, STREAM_NOISE_A, r, k);
+            sm.st.an[k] = z;
+            if (r == kp.n_burn) {
+                reinterpret_cast<double2*>(st.noise_a)[(size_t)e * A + k] = z;
+            } else {
+                sm.act[k] = inj ? reinterpret_cast<const double2*>(dr.burn_actions)[((size_t)e * kp.n_burn + r) * A + k]
+                                : draw_normal2(ctx, STREAM_BURN, r, k);
+            }
         }
-        g.sync();
-        env_step<MODE, PRECISE>(sm, kp, g, nx, nullptr);
+        if (r == kp.n_burn) break;
+        env_step<MODE, PRECISE>(sm, kp, g, nullptr);
     }
     g.sync();
 }
@@ -412,23 +621,25 @@ __device__ __forceinline__ void raster_zero_fill(float* __restrict__ grid_e, int
     }
 }
 
-// SwarmStateProcessor.process_state (state_processors.py:25-42) of the positions xs (N) / as (A) in
-// shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
-// The grid must have been zero-filled (raster_zero_fill) before a barrier that precedes this call.
-// Uses sm.table / sm.cid / sm.box (the force scratch must be dead unless they do not alias).
-__device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ xs, const double2* __restrict__ as,
-                                           const KP& kp, const Grp& g, float* __restrict__ grid_e,
-                                           uint8_t* __restrict__ pos_e) {
-    const int N = kp.N, A = kp.A, G = kp.G, P = N + A, cells = G * G;
+// One-time clear of the counter table (afterwards env_raster leaves it clean).
+__device__ __forceinline__ void raster_table_clear(const Smem& sm, int cells, const RGrp& g) {
+    for (int i = g.tid; i < cells; i += g.n) sm.table[i] = 0u;
+}
+
+// SwarmStateProcessor.process_state (state_processors.py:25-42) of the points pts = [N locusts; A
+// agents] in shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
+// Preconditions: grid_e zero-filled by this group (raster_zero_fill), sm.table all zero and pts
+// visible (a barrier since).  Postcondition: sm.table all zero again, after a group barrier.
+__device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const RGrp& g,
+                                           float* __restrict__ grid_e, uint8_t* __restrict__ pos_e) {
+    const int N = kp.N, A = kp.A, G = kp.G, P = N + A;
     // phase 0: one thread walks the sequential FP64 mean (np.mean(vstack([x,xa]),axis=0)[0] is a
-    // plain left-to-right sum, ~23 cycles per dependent DADD); everyone else clears the counters.
+    // plain left-to-right sum, ~23 cycles per dependent DADD)
     if (g.tid == 0) {
         double s = 0.0;
-        for (int i = 0; i < N; ++i) s = __dadd_rn(s, xs[i].x);
-        for (int k = 0; k < A; ++k) s = __dadd_rn(s, as[k].x);
+#pragma unroll 8
+        for (int i = 0; i < P; ++i) s = __dadd_rn(s, pts[i].x);
         sm.box[0] = s / (double)P;
-    } else {
-        for (int i = g.tid - 1; i < cells; i += g.n - 1) sm.table[i] = 0u;
     }
     g.sync();
     // phase 1: bin every point in FP64 against numpy's edges, count with warp-aggregated atomics
@@ -444,7 +655,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
         int cell = 0;
         if (p < P) {
             const bool agent = p >= N;
-            const double2 q = agent ? as[p - N] : xs[p];
+            const double2 q = pts[p];
             const int cx = count_le(q.x, lo_x, hi_x, step_x, inv_x, G);
             const int cy = count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
             if (agent) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
@@ -468,16 +679,18 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
         if (p < P) sm.cid[p] = mine;
     }
     g.sync();
-    // phase 2: sparse scatter of the non-zero cells over the zero fill
+    // phase 2: sparse scatter of the non-zero cells over the zero fill; the writer cleans its counter
     float2* g2 = reinterpret_cast<float2*>(grid_e);
     for (int p = g.tid; p < P; p += g.n) {
         const int c = sm.cid[p];
         if (c >= 0) {
             const uint32_t w = sm.table[c];
+            sm.table[c] = 0u;
             g2[c] = make_float2(__fdiv_rn((float)(w & 0xffffu), (float)N),
                                 A > 0 ? __fdiv_rn((float)(w >> 16), (float)A) : 0.f);
         }
     }
+    g.sync();
 }
 
 }  // namespace swarm

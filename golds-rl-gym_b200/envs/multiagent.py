@@ -99,7 +99,12 @@ class BatchedSwarmEnv(object):
         self.positions = torch.zeros(E, A, 2, dtype=torch.uint8, device=d)
         self.state_c = nat.SwarmState(_ptr(self.x), _ptr(self.xa), _ptr(self.noise_x), _ptr(self.noise_a),
                                       _ptr(self.elapsed), _ptr(self.episode))
-        self._host = None
+        self._io = nat.SwarmStepIO()
+        self._io.reward, self._io.done = self.reward.data_ptr(), self.done_u8.data_ptr()
+        self._grid_ptr, self._pos_ptr = self.grid.data_ptr(), self.positions.data_ptr()
+        self._params_ref, self._state_ref, self._io_ref = (ctypes.byref(self.params), ctypes.byref(self.state_c),
+                                                           ctypes.byref(self._io))
+        self._done_view = self.done_u8.view(torch.bool)
         self._was_reset = False
 
     # ------------------------------------------------------------------ gym surface
@@ -132,24 +137,28 @@ class BatchedSwarmEnv(object):
         rasterize = self.rasterize if rasterize is None else rasterize
         auto_reset = self.auto_reset if auto_reset is None else auto_reset
         flags = (nat.SWARM_STEP_AUTO_RESET if auto_reset else 0) | (nat.SWARM_STEP_CLIP_ACTIONS if clip else 0)
-        io = nat.SwarmStepIO()
-        if actions.dtype == torch.float64:
-            io.actions_f64 = _ptr(actions)
+        io = self._io                      # one persistent SwarmStepIO; only the per-call fields change
+        if actions.dtype == torch.float32:
+            io.actions_f32, io.actions_f64 = actions.data_ptr(), None
+        elif actions.dtype == torch.float64:
+            io.actions_f32, io.actions_f64 = None, actions.data_ptr()
             flags |= nat.SWARM_STEP_ACTIONS_F64
-        elif actions.dtype == torch.float32:
-            io.actions_f32 = _ptr(actions)
         else:
             raise ValueError("actions must be float32 or float64")
-        io.noise_a, io.noise_x = _ptr(noise_a), _ptr(noise_x)
-        io.reward, io.done = _ptr(self.reward), _ptr(self.done_u8)
+        io.noise_a = noise_a.data_ptr() if noise_a is not None else None
+        io.noise_x = noise_x.data_ptr() if noise_x is not None else None
         if rasterize:
-            io.grid, io.positions = _ptr(self.grid), _ptr(self.positions)
-        io.v_out = _ptr(v_out)
+            io.grid, io.positions = self._grid_ptr, self._pos_ptr
+        else:
+            io.grid, io.positions = None, None
+        io.v_out = v_out.data_ptr() if v_out is not None else None
         io.flags = flags
-        nat.check(self.lib.swarm_step(ctypes.byref(self.params), ctypes.byref(self.state_c), ctypes.byref(io),
-                                      ctypes.byref(reset_draws.c) if reset_draws is not None else None,
-                                      _stream(self.device)), "swarm_step")
-        return (self.x, self.xa), self.reward, self.done_u8.view(torch.bool), {}
+        rc = self.lib.swarm_step(self._params_ref, self._state_ref, self._io_ref,
+                                 ctypes.byref(reset_draws.c) if reset_draws is not None else None,
+                                 torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            nat.check(rc, "swarm_step")
+        return (self.x, self.xa), self.reward, self._done_view, {}
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) form
     def step_host(self, host_actions, host_reward, host_done):

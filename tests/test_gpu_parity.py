@@ -101,6 +101,37 @@ def test_forces_match_oracle(M, name, mode):
     assert (r < 0).all()
 
 
+@pytest.mark.parametrize("mode", ["fast", "precise"])
+@pytest.mark.parametrize("N", [1, 31, 33, 96, 100, 128, 192, 320, 448, 512, 513, 1100])
+def test_forces_and_step_every_tiling(M, N, mode):
+    """Every force-kernel shape: 32-wide tiles (odd / even tile counts), 64-wide super-tiles (1, 2, 3,
+    5, 7, 8 of them), ordered pairs with 2 and 4 targets per thread, ragged last tiles.  v_calculate and one
+    full step against the oracle on a post-burn-in state."""
+    E = 3
+    draws = stack_draws([4200 + N + e for e in range(E)], N)
+    x, xa = so.reset_injected(*draws)
+    na, nx = draws[3][:, 10], draws[4][:, 10]
+    env = M.BatchedSwarmEnv(E, n_locusts=N, max_episode_steps=0, math_mode=mode, auto_reset=False, rasterize=True)
+    v, r = env.forces(to_dev(x), to_dev(xa))
+    v_ref, r_ref = so.forces(x, xa)
+    v, r = v.cpu().numpy(), r.cpu().numpy()
+    for e in range(E):
+        assert rel_err(v[e], v_ref[e]) <= RTOL, (N, e)
+    assert np.all(np.abs(r - r_ref) <= RTOL * np.abs(r_ref))
+    a = clipped(np.random.RandomState(N), (E, 10, 2))
+    load_state(env, x, xa, na, nx)
+    (gx, gxa), gr, gd, _ = env.step(to_dev(a))
+    rew, done = so.step(x, xa, a.astype(np.float64), na, nx)
+    gx, gxa = gx.cpu().numpy(), gxa.cpu().numpy()
+    assert np.array_equal(gxa, xa)
+    for e in range(E):
+        assert rel_err(gx[e], x[e]) <= STEP_TOL, (N, e)
+        g, p_ = so.rasterize(gx[e], gxa[e], 84)
+        assert np.array_equal(env.grid[e].cpu().numpy(), g.astype(np.float32))
+        assert np.array_equal(env.positions[e].cpu().numpy(), p_)
+    assert np.all(np.abs(gr.cpu().numpy() - rew) <= RTOL * np.abs(rew))
+
+
 @pytest.mark.parametrize("N", [64, 80])
 def test_reset_and_free_running_16_distribution(M, N):
     """Free-running parity: injected reset (10 burn-in steps) then 16 steps, 128 seeds.
