@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -23,11 +24,7 @@ __device__ __forceinline__ void prefetch_env(const Stage& sg, const KP& kp, cons
                                              const int e, const Grp& g) {
     const int N = kp.N, A = kp.A;
     const double2* gx = reinterpret_cast<const double2*>(st.x) + (size_t)e * N;
-    const double2* gnx = reinterpret_cast<const double2*>(io.noise_x ? io.noise_x : st.noise_x) + (size_t)e * N;
-    for (int i = g.tid; i < N; i += g.n) {
-        cp_async<16>(sg.xs + i, gx + i);
-        cp_async<16>(sg.nx + i, gnx + i);
-    }
+    for (int i = g.tid; i < N; i += g.n) cp_async<16>(sg.xs + i, gx + i);
     const double2* ga = reinterpret_cast<const double2*>(st.xa) + (size_t)e * A;
     const double2* gna = reinterpret_cast<const double2*>(io.noise_a ? io.noise_a : st.noise_a) + (size_t)e * A;
     for (int k = g.tid; k < A; k += g.n) {
@@ -39,7 +36,6 @@ __device__ __forceinline__ void prefetch_env(const Stage& sg, const KP& kp, cons
             cp_async<8>(sg.araw + 16 * k, reinterpret_cast<const float2*>(io.actions_f32) + (size_t)e * A + k);
     }
     if (g.tid == g.n - 1) cp_async<4>(sg.misc, st.elapsed + e);
-    cp_async_commit();
 }
 
 // SwarmEnv._step + TimeLimit + SwarmRunner auto-reset + process_state for the whole batch.
@@ -63,14 +59,27 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
 
     if ((int)threadIdx.x < n_force) {
         const Grp g = {(int)threadIdx.x, n_force};
+        constexpr int T = ModeT<MODE>::T;
         if ((int)blockIdx.x < kp.E) prefetch_env(stage_at(smem_raw, N, A, 0), kp, st, io, blockIdx.x, g);
+        cp_async_commit();
         int it = 0;
         for (int e = blockIdx.x; e < kp.E; e += gridDim.x, ++it) {
             sm.st = stage_at(smem_raw, N, A, it & 1);
             cp_async_wait_all();
-            g.sync();      // this env's stage buffer has landed; the other one is free again
+            g.sync();      // this env's stage buffer has landed; the other one and sm.nx are free again
+            {   // this env's locust noise row: each thread fetches the rows of its own targets, so that its
+                // own wait (before the integration) is all the synchronisation it needs
+                const double2* gnx = reinterpret_cast<const double2*>(io.noise_x ? io.noise_x : st.noise_x) + (size_t)e * N;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const int j = target_index<MODE>(g, t);
+                    if (j < N) cp_async<16>(sm.nx + j, gnx + j);
+                }
+                cp_async_commit();
+            }
             if (e + (int)gridDim.x < kp.E)
                 prefetch_env(stage_at(smem_raw, N, A, (it + 1) & 1), kp, st, io, e + gridDim.x, g);
+            cp_async_commit();     // (possibly empty) group of the next env: env_step waits for all but this one
 
             // actions: HBM dtype -> FP64, optional clip (the owner thread of agent k also moves it)
             for (int k = g.tid; k < A; k += g.n) {
@@ -102,31 +111,41 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                 sm.act[k] = a;
             }
 
-            const double reward = env_step<MODE, PRECISE>(sm, kp, g, io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr);
-
-            // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
-            int elapsed = sm.st.misc[0] + 1;
-            const bool done = (reward >= 0.0) || (kp.max_steps > 0 && elapsed >= kp.max_steps);
-            if (g.tid == 0) {
-                io.reward[e] = (float)reward;
-                io.done[e] = done ? 1 : 0;
-            }
-            if (done && (io.flags & SWARM_STEP_AUTO_RESET)) {
-                // emulator_runner.py:127-132: the terminal reward/done are reported, the state (and
-                // therefore the observation) is the freshly reset episode's.  Group-uniform branch.
-                const uint32_t ep = st.episode[e];
-                env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
-                elapsed = 0;
-                if (g.tid == 0) st.episode[e] = ep + 1;
+            // One env_step call site serves the step proper and, if the episode ends here, the burn-in
+            // steps of the auto-reset (emulator_runner.py:127-132: the terminal reward/done are reported,
+            // the state -- and therefore the observation -- is the freshly reset episode's).
+            int elapsed = 0;
+            ResetCtx rc;
+            uint32_t ep = 0;
+            int r = -1;                              // -1: the step proper; >= 0: burn-in row being stepped
+            float* v_out = io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr;
+            for (;;) {
+                const double reward = env_step<MODE, PRECISE>(sm, kp, g, v_out);
+                if (r < 0) {
+                    // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
+                    elapsed = sm.st.misc[0] + 1;
+                    const bool done = (reward >= 0.0) || (kp.max_steps > 0 && elapsed >= kp.max_steps);
+                    if (g.tid == 0) {
+                        io.reward[e] = (float)reward;
+                        io.done[e] = done ? 1 : 0;
+                    }
+                    if (!(done && (io.flags & SWARM_STEP_AUTO_RESET))) break;      // group-uniform
+                    ep = st.episode[e];
+                    rc = reset_begin(sm, kp, g, e, ep, has_draws != 0, dr);
+                    v_out = nullptr;
+                    elapsed = 0;
+                }
+                if (reset_row(sm, kp, g, rc, ++r, dr, st)) {
+                    if (g.tid == 0) st.episode[e] = ep + 1;
+                    break;
+                }
             }
             if (g.tid == 0) st.elapsed[e] = elapsed;
 
-            if (raster && it >= 2) {   // wait until the raster group has let go of rx[it & 1] (two envs ago)
-                if (it & 1) bar_sync<BAR_EMPTY1>(n_all); else bar_sync<BAR_EMPTY0>(n_all);
-            }
+            if (raster && it >= 1) bar_sync<BAR_EMPTY>(n_all);   // the raster group has read the previous env's points
             double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * N;
             double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
-            double2* rx = (it & 1) ? sm.rx[1] : sm.rx[0];
+            double2* rx = sm.rx;
             for (int i = g.tid; i < N; i += g.n) {
                 const double2 q = sm.st.xs[i];
                 ox[i] = q;
@@ -139,24 +158,34 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             }
             if (raster) {
                 __threadfence_block();
-                if (it & 1) bar_arrive<BAR_FULL1>(n_all); else bar_arrive<BAR_FULL0>(n_all);
+                bar_arrive<BAR_FULL>(n_all);
             }
         }
     } else {
         const RGrp g = {(int)threadIdx.x - n_force, n_raster};
         const int cells = kp.G * kp.G;
-        raster_table_clear(sm, cells, g);
-        int it = 0;
-        for (int e = blockIdx.x; e < kp.E; e += gridDim.x, ++it) {
+        const bool tma = tma_zero_fill_ok(io.grid, cells);
+        const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
+        raster_table_clear(sm, (int)(table_bytes / 4), g);
+        g.sync();
+        for (int e = blockIdx.x; e < kp.E; e += gridDim.x) {
+            const bool more = e + (int)gridDim.x < kp.E;     // the force group will wait for the buffer again
             float* grid_e = io.grid + (size_t)e * cells * 2;
-            // The observation is ~99 % zeros: stream them out while the force group still computes;
-            // the non-zero cells are scattered over them afterwards.
-            raster_zero_fill(grid_e, cells, g.tid, g.n);
-            if (it & 1) bar_sync<BAR_FULL1>(n_all); else bar_sync<BAR_FULL0>(n_all);
-            env_raster(sm, (it & 1) ? sm.rx[1] : sm.rx[0], kp, g, grid_e, io.positions + (size_t)e * A * 2);
-            if (e + 2 * (int)gridDim.x < kp.E) {   // the force group will wait for this buffer again
-                if (it & 1) bar_arrive<BAR_EMPTY1>(n_all); else bar_arrive<BAR_EMPTY0>(n_all);
+            // The observation is ~99 % zeros: stream them out while the force group still computes
+            // (TMA bulk stores fed from the clean counter table, else plain stores); the non-zero cells
+            // are scattered over them afterwards.
+            const bool xp_nozf = io.flags & 256u, xp_noraster = io.flags & 512u;   // EXPERIMENT
+            if (!xp_nozf) {
+            if (tma) {
+                if (g.tid == 0) tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
+            } else {
+                raster_zero_fill(grid_e, cells, g.tid, g.n);
             }
+            }
+            bar_sync<BAR_FULL>(n_all);
+            auto release = [more, n_all]() { if (more) bar_arrive<BAR_EMPTY>(n_all); };
+            if (!xp_noraster) env_raster(sm, sm.rx, kp, g, grid_e, io.positions + (size_t)e * A * 2, tma && !xp_nozf, release);
+            else release();
         }
     }
 }
@@ -171,7 +200,8 @@ __global__ void __maxnreg__(64) k_reset(const KP kp, const SwarmState st, const 
     const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM);
     const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const uint32_t ep = st.episode[e];
-    env_reset<MODE, PRECISE>(sm, kp, g, e, ep, has_draws != 0, dr, st);
+    const ResetCtx rc = reset_begin(sm, kp, g, e, ep, has_draws != 0, dr);
+    for (int r = 0; !reset_row(sm, kp, g, rc, r, dr, st); ++r) env_step<MODE, PRECISE>(sm, kp, g, nullptr);
     double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * kp.N;
     double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * kp.A;
     for (int i = g.tid; i < kp.N; i += g.n) ox[i] = sm.st.xs[i];
@@ -194,13 +224,13 @@ __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __
     float* grid_e = grid + (size_t)e * cells * 2;
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
-    double2* pts = sm.rx[0];
+    double2* pts = sm.rx;
     for (int i = g.tid; i < kp.N; i += g.n) pts[i] = gx[i];
     for (int k = g.tid; k < kp.A; k += g.n) pts[kp.N + k] = ga[k];
     raster_zero_fill(grid_e, cells, g.tid, g.n);
-    raster_table_clear(sm, cells, g);
+    raster_table_clear(sm, (int)(smem_table_bytes(kp.N, kp.A, kp.G) / 4), g);
     g.sync();
-    env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2);
+    env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, NoRelease());
     if (box && g.tid == 0) {
         const double m = sm.box[0];
         box[4 * e + 0] = m - kp.half_w;
@@ -514,11 +544,12 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (!io->reward || !io->done) return SWARM_ERR_NULL;
     if ((io->flags & SWARM_STEP_ACTIONS_F64) ? !io->actions_f64 : !io->actions_f32) return SWARM_ERR_NULL;
     if ((io->grid != nullptr) != (io->positions != nullptr)) return SWARM_ERR_FLAGS;
-    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
+    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64 | 768u)) return SWARM_ERR_FLAGS;
     if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
     const bool raster = io->grid != nullptr;
-    const size_t smem = step_smem(p, raster);
+    size_t smem = step_smem(p, raster);
+    if (const char* pad = getenv("SWARM_EXP_PAD_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
     const int nf = block_threads(kp.N);
     const int nt = nf + (raster ? raster_threads(kp.N, kp.A) : 0);
     const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;

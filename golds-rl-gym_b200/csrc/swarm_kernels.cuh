@@ -47,11 +47,11 @@ struct KP {
     uint32_t env_off;
 };
 
-// One STAGE buffer = everything the step of one env reads from HBM:
-//   x (N) | noise_x (N) | xa (A) | noise_a (A) | raw actions (A x 16 B) | misc (16 B: elapsed)
+// One STAGE buffer = what is prefetched for the step of one env (the locust noise row follows
+// later, straight into Smem::nx):
+//   x (N) | xa (A) | noise_a (A) | raw actions (A x 16 B) | misc (16 B: elapsed)
 struct Stage {
     double2* xs;            // N   locust positions (FP64 integrator state, updated in place)
-    double2* nx;            // N   locust noise row of the current step (unscaled)
     double2* as;            // A   agent positions
     double2* an;            // A   agent noise row
     unsigned char* araw;    // A x 16 B: the env's actions as they sit in HBM (f32 pair or f64 pair)
@@ -60,6 +60,7 @@ struct Stage {
 
 struct Smem {
     Stage st;         // the stage buffer of the env being stepped
+    double2* nx;      // N   locust noise row of the current step (unscaled)
     double2* act;     // A   actions after conversion / clipping
     double* red;      // 32  reduction scratch
     double* box;      // 2   rasteriser: mean x
@@ -69,21 +70,30 @@ struct Smem {
                       //   MODE 2/4: N locusts + A agents
     float2* slot;     // MODE 1/3: nt x nslots x 32 reaction-force partial sums
     // ---- rasteriser (present when the kernel rasterises)
-    double2* rx[2];   // 2 x (N+A): post-step positions handed from the force to the raster group
-    uint32_t* table;  // G*G packed cell counters: lo16 locusts, hi16 agents
+    double2* rx;      // N+A: post-step positions handed from the force to the raster group
+    uint32_t* table;  // G*G packed cell counters, 16 bits per cell (two cells per word): locusts in the low
+                      // bits, agents above them (kAgentShift); 32 bits per cell (locusts lo16, agents hi16)
+                      // when the counts do not fit
     int* cid;         // N+A: cell written out by this point (or -1)
 };
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
 __host__ __device__ inline int n_tiles(int N) { return (N + 31) >> 5; }
 
-__host__ __device__ inline size_t smem_stage_bytes(int N, int A) { return 16 * ((size_t)2 * N + 3 * A + 1); }
+__host__ __device__ inline size_t smem_stage_bytes(int N, int A) { return 16 * ((size_t)N + 3 * A + 1); }
 __host__ __device__ inline int sym_tiles(int N, int sym);
 __host__ __device__ inline size_t smem_src_bytes(int N, int A, int sym) {
     return smem_align(sizeof(float4) * (sym ? (size_t)sym_tiles(N, sym) * 64 + A : (size_t)N + A));
 }
-__host__ __device__ inline size_t smem_fixed_bytes(int A) {
-    return smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) + smem_align(sizeof(double) * 2);
+__host__ __device__ inline size_t smem_fixed_bytes(int N, int A) {
+    return smem_align(sizeof(double2) * N) + smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) +
+           smem_align(sizeof(double) * 2);
+}
+// 16-bit cell counters hold (locusts | agents << kAgentShift) when N < 2^kAgentShift and A < 2^(16-kAgentShift)
+constexpr int kAgentShift = 11;
+__host__ __device__ inline bool table_is16(int N, int A) { return N < (1 << kAgentShift) && A < (1 << (16 - kAgentShift)); }
+__host__ __device__ inline size_t smem_table_bytes(int N, int A, int G) {
+    return table_is16(N, A) ? smem_align(sizeof(uint16_t) * G * G) : smem_align(sizeof(uint32_t) * G * G);
 }
 // sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3)
 __host__ __device__ inline int sym_tiles(int N, int sym) { return sym == 2 ? 2 * ((N + 63) >> 6) : n_tiles(N); }
@@ -95,12 +105,11 @@ __host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym) {
            (sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * sym_slots(N, sym) * 32) : 0);
 }
 __host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G) {
-    return 2 * smem_align(sizeof(double2) * (N + A)) + smem_align(sizeof(uint32_t) * G * G) +
-           smem_align(sizeof(int) * (N + A));
+    return smem_align(sizeof(double2) * (N + A)) + smem_table_bytes(N, A, G) + smem_align(sizeof(int) * (N + A));
 }
 // n_stage: stage buffers (2 in the pipelined step kernel, 1 in reset/forces, 0 in the rasteriser)
 __host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, bool raster, int sym) {
-    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(A) + (force ? smem_force_bytes(N, A, sym) : 0) +
+    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(N, A) + (force ? smem_force_bytes(N, A, sym) : 0) +
            (raster ? smem_raster_bytes(N, A, G) : 0);
 }
 
@@ -108,8 +117,7 @@ __device__ __forceinline__ Stage stage_at(unsigned char* base, int N, int A, int
     unsigned char* p = base + (size_t)b * smem_stage_bytes(N, A);
     Stage s;
     s.xs = reinterpret_cast<double2*>(p);
-    s.nx = s.xs + N;
-    s.as = s.nx + N;
+    s.as = s.xs + N;
     s.an = s.as + A;
     s.araw = reinterpret_cast<unsigned char*>(s.an + A);
     s.misc = reinterpret_cast<int*>(s.araw + 16 * (size_t)A);
@@ -120,15 +128,15 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     Smem s;
     s.st = stage_at(base, N, A, 0);
     size_t o = (size_t)n_stage * smem_stage_bytes(N, A);
+    s.nx = reinterpret_cast<double2*>(base + o);  o += smem_align(sizeof(double2) * N);
     s.act = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * A);
     s.red = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 32);
     s.box = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 2);
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
     if (force) o += smem_force_bytes(N, A, sym);
-    s.rx[0] = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * (N + A));
-    s.rx[1] = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * (N + A));
-    s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_align(sizeof(uint32_t) * G * G);
+    s.rx = reinterpret_cast<double2*>(base + o);    o += smem_align(sizeof(double2) * (N + A));
+    s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_table_bytes(N, A, G);
     s.cid = reinterpret_cast<int*>(base + o);
     return s;
 }
@@ -142,6 +150,8 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all but the most recently committed group have landed
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // multiagent.py:70-86  x_update = cutoff; x += dt*v + noise; cutoff   (FP64, no FMA contraction
@@ -158,7 +168,7 @@ __device__ __forceinline__ void move_particle(double2& p, double2 v, double2 n, 
 }
 
 // Named barriers (bar.sync id, n) of the warp-specialised step kernel.  0 stays __syncthreads.
-enum : int { BAR_FORCE = 1, BAR_RASTER = 2, BAR_FULL0 = 3, BAR_FULL1 = 4, BAR_EMPTY0 = 5, BAR_EMPTY1 = 6 };
+enum : int { BAR_FORCE = 1, BAR_RASTER = 2, BAR_FULL = 3, BAR_EMPTY = 4 };
 
 template <int ID>
 __device__ __forceinline__ void bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
@@ -265,17 +275,20 @@ __device__ __forceinline__ void stage_locusts(const Smem& sm, const KP& kp, cons
     }
 }
 
-// Rotation steps K0..K1 of one tile pair: in step k lane l meets element (l+k)%32 of the other
-// tile (read wrap-free from the doubled tile).  The own force accumulates in (ax,ay); the
-// reaction on the met element accumulates in (bx,by), which moves one lane down per step so
-// that it follows its element.  On return lane l holds the reaction for element (l+K1)%32.
-template <int K0, int K1, bool PRECISE>
-__device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const float4 tg, const KP& kp, const int nxt,
-                                         float& ax, float& ay, float& bx, float& by) {
-    bx = 0.f;
-    by = 0.f;
-#pragma unroll 8
-    for (int k = K0; k <= K1; ++k) {
+constexpr int kTileUnroll = 4;   // rotation steps unrolled together (x targets per lane = pair chains in flight)
+
+// n rotation steps of one tile pass.  tl points at the first element this lane meets (inside a
+// doubled tile, so tl[k] is element (first+k)%32 without wrap logic).  The own force accumulates
+// in (ax,ay); (bx,by) is the reaction on the met element and moves one lane down BEFORE every
+// step (also before the first one: it then carries zeros, or the caller's partial sum), so that
+// it follows its element.  On return lane l holds the reaction for the element met last.
+template <bool PRECISE>
+__device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const int n, const float4 tg, const KP& kp,
+                                         const int nxt, float& ax, float& ay, float& bx, float& by) {
+#pragma unroll kTileUnroll
+    for (int k = 0; k < n; ++k) {
+        bx = __shfl_sync(kFull, bx, nxt);
+        by = __shfl_sync(kFull, by, nxt);
         const float4 q = tl[k];
         const float dx = (q.x - tg.x) + (q.z - tg.z);
         const float dy = (q.y - tg.y) + (q.w - tg.w);
@@ -284,44 +297,43 @@ __device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const fl
         ay = fmaf(w, dy, ay);
         bx = fmaf(-w, dx, bx);
         by = fmaf(-w, dy, by);
-        if (k < K1) {
-            bx = __shfl_sync(kFull, bx, nxt);
-            by = __shfl_sync(kFull, by, nxt);
-        }
     }
 }
 
 // MODE 1, part 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I
-// meets tiles I+1..I+floor((nt-1)/2) fully, tile I+nt/2 (nt even) half each way, and itself.
-// The reaction sums land in sm.slot; the caller must barrier before forces_sym_finish.
+// meets itself (lane offsets 1..15 with reaction, offset 16 one way: each such pair appears in two
+// lanes, offset 0 = self), tiles I+1..I+floor((nt-1)/2) fully and tile I+nt/2 (nt even) half each
+// way.  One loop over these passes, so the pair code exists once.  The reaction sums land in
+// sm.slot; the caller must barrier before forces_sym_finish.
 template <bool PRECISE>
 __device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
     const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
     const int nxt = (lane + 1) & 31;
+    const int nfull = (nt - 1) >> 1;
     const float4* S = sm.src;
     const float4 tg = S[I * 64 + lane];
-    float bx, by;
     ax = 0.f;
     ay = 0.f;
-    // own tile: offsets 1..15 both ways, offset 16 one way (each such pair appears in two lanes), offset 0 = self
-    tile_sym<1, 15, PRECISE>(S + I * 64 + lane, tg, kp, nxt, ax, ay, bx, by);
-    sm.slot[(I * nslots) * 32 + ((lane + 15) & 31)] = make_float2(bx, by);
     pair_ordered<PRECISE>(S[I * 64 + lane + 16], tg, kp, ax, ay);
-    const int nfull = (nt - 1) >> 1;
-    for (int o = 1; o <= nfull; ++o) {
-        int B = I + o;
-        if (B >= nt) B -= nt;
-        tile_sym<0, 31, PRECISE>(S + B * 64 + lane, tg, kp, nxt, ax, ay, bx, by);
-        sm.slot[(B * nslots + o) * 32 + ((lane + 31) & 31)] = make_float2(bx, by);
-    }
-    if ((nt & 1) == 0) {
-        // lane offsets 0..15 from the lower tile, 16..31 (= 1..16 seen from the partner) from the upper
-        const int o = nt >> 1;
-        const int B = I < o ? I + o : I - o;
-        const int koff = I < o ? 0 : 1;
-        tile_sym<0, 15, PRECISE>(S + B * 64 + lane + koff, tg, kp, nxt, ax, ay, bx, by);
-        sm.slot[(B * nslots + o) * 32 + ((lane + 15 + koff) & 31)] = make_float2(bx, by);
+#pragma unroll 1
+    for (int o = 0; o < nslots; ++o) {
+        int B = I, first = 1, n = 15;                    // own tile
+        if (o > 0) {
+            if (o <= nfull) {                            // a full tile pair
+                B = I + o;
+                if (B >= nt) B -= nt;
+                first = 0;
+                n = 32;
+            } else {   // lane offsets 0..15 from the lower tile, 16..31 (= 1..16 seen from the partner) from the upper
+                B = I < o ? I + o : I - o;
+                first = I < o ? 0 : 1;
+                n = 16;
+            }
+        }
+        float bx = 0.f, by = 0.f;
+        tile_sym<PRECISE>(S + B * 64 + lane + first, n, tg, kp, nxt, ax, ay, bx, by);
+        sm.slot[(B * nslots + o) * 32 + ((lane + first + n - 1) & 31)] = make_float2(bx, by);
     }
 }
 
@@ -355,77 +367,75 @@ __device__ __forceinline__ void pair_sym(const float4 q, const float4 tg, const 
     }
 }
 
-// Rotation steps K0..K1 against one doubled half-tile tl (= S + H*64 + lane): in step k the lane
-// meets element (lane+k)%32 and evaluates it against its A and/or B target; (bx,by) is the
-// reaction on the met element and moves one lane down per step.  CONT: (bx,by) continues from an
-// earlier call (shuffle before the first step too).  On return lane l holds element (l+K1)%32's.
-template <int K0, int K1, bool DO_A, bool DO_B, bool REACT_A, bool REACT_B, bool CONT, bool PRECISE>
-__device__ __forceinline__ void tile2(const float4* __restrict__ tl, const float4 tgA, const float4 tgB, const KP& kp,
-                                      const int nxt, float& aAx, float& aAy, float& aBx, float& aBy, float& bx,
-                                      float& by) {
-#pragma unroll 8
-    for (int k = K0; k <= K1; ++k) {
-        if ((REACT_A || REACT_B) && (CONT || k > K0)) {
-            bx = __shfl_sync(kFull, bx, nxt);
-            by = __shfl_sync(kFull, by, nxt);
-        }
+// n rotation steps of one half-tile pass with both targets (see tile_sym for the conventions).
+template <bool PRECISE>
+__device__ __forceinline__ void tile_sym2(const float4* __restrict__ tl, const int n, const float4 tgA, const float4 tgB,
+                                          const KP& kp, const int nxt, float& aAx, float& aAy, float& aBx, float& aBy,
+                                          float& bx, float& by) {
+#pragma unroll kTileUnroll
+    for (int k = 0; k < n; ++k) {
+        bx = __shfl_sync(kFull, bx, nxt);
+        by = __shfl_sync(kFull, by, nxt);
         const float4 q = tl[k];
-        if (DO_A) pair_sym<REACT_A, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
-        if (DO_B) pair_sym<REACT_B, PRECISE>(q, tgB, kp, aBx, aBy, bx, by);
+        pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
+        pair_sym<true, PRECISE>(q, tgB, kp, aBx, aBy, bx, by);
     }
 }
 
 // MODE 3, part 1.  Warp I owns super-tile I = half-tiles 2I (A targets) and 2I+1 (B targets).
-//   own super-tile: A x A and B x B by offsets 1..15 both ways + 16 one way; A x B split by offset:
-//                   (B target, A source) for offsets 0..15, (A target, B source) for 1..16;
-//   super-tiles I+1 .. I+floor((nt2-1)/2): all 64 x 64 pairs;  I+nt2/2 (nt2 even): half each way.
+// Passes (one loop, so the pair code exists once):
+//   p = 0  own A half as sources: offset 0 (B target only: the A x B block is split by offset, (B target,
+//          A source) takes 0..15), offsets 1..15 both targets, offset 16 A target one way;
+//   p = 1  own B half as sources: offsets 1..15 both targets, offset 16 A target ((A target, B source)
+//          takes 1..16) with reaction + B target one way;
+//   then   super-tiles I+1 .. I+floor((nt2-1)/2): both halves, all 32 offsets;
+//          super-tile I+nt2/2 (nt2 even): both halves, half the offsets each way.
 template <bool PRECISE>
 __device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
                                                    float (&vy)[2]) {
     const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
     const int nxt = (lane + 1) & 31;
-    const float4* S = sm.src;
-    const float4* tlA = S + (2 * I) * 64 + lane;
-    const float4* tlB = tlA + 64;
-    const float4 tgA = tlA[0], tgB = tlB[0];
-    float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f, bx = 0.f, by = 0.f;
-    // sources = own A half
-    tile2<0, 0, false, true, false, true, false, PRECISE>(tlA, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-    tile2<1, 15, true, true, true, true, true, PRECISE>(tlA, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-    sm.slot[((2 * I) * nslots) * 32 + ((lane + 15) & 31)] = make_float2(bx, by);
-    tile2<16, 16, true, false, false, false, false, PRECISE>(tlA, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-    // sources = own B half
-    bx = 0.f; by = 0.f;
-    tile2<1, 15, true, true, true, true, false, PRECISE>(tlB, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-    tile2<16, 16, true, true, true, false, true, PRECISE>(tlB, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-    sm.slot[((2 * I + 1) * nslots) * 32 + ((lane + 16) & 31)] = make_float2(bx, by);
     const int nfull = (nt2 - 1) >> 1;
-    for (int o = 1; o <= nfull; ++o) {
-        int J = I + o;
-        if (J >= nt2) J -= nt2;
+    const int npass = 2 * nslots;
+    const float4* S = sm.src;
+    const float4 tgA = S[(2 * I) * 64 + lane], tgB = S[(2 * I + 1) * 64 + lane];
+    float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int H = 2 * J + h;
-            bx = 0.f; by = 0.f;
-            tile2<0, 31, true, true, true, true, false, PRECISE>(S + H * 64 + lane, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy,
-                                                                 bx, by);
-            sm.slot[(H * nslots + o) * 32 + ((lane + 31) & 31)] = make_float2(bx, by);
+    for (int p = 0; p < npass; ++p) {
+        const int o = p >> 1, h = p & 1;
+        int J = I, first = 1, n = 15;
+        if (o > 0) {
+            if (o <= nfull) {
+                J = I + o;
+                if (J >= nt2) J -= nt2;
+                first = 0;
+                n = 32;
+            } else {
+                J = I < o ? I + o : I - o;
+                first = I < o ? 0 : 1;
+                n = 16;
+            }
         }
-    }
-    if ((nt2 & 1) == 0) {
-        // lane offsets 0..15 from the lower super-tile, 16..31 (= 1..16 seen from the partner) from the upper
-        const int o = nt2 >> 1;
-        const int J = I < o ? I + o : I - o;
-        const int koff = I < o ? 0 : 1;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int H = 2 * J + h;
-            bx = 0.f; by = 0.f;
-            tile2<0, 15, true, true, true, true, false, PRECISE>(S + H * 64 + lane + koff, tgA, tgB, kp, nxt, aAx, aAy, aBx,
-                                                                 aBy, bx, by);
-            sm.slot[(H * nslots + o) * 32 + ((lane + 15 + koff) & 31)] = make_float2(bx, by);
+        const int H = 2 * J + h;
+        const float4* tl = S + H * 64 + lane;
+        float bx = 0.f, by = 0.f;
+        if (p == 0) pair_sym<true, PRECISE>(tl[0], tgB, kp, aBx, aBy, bx, by);
+        tile_sym2<PRECISE>(tl + first, n, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+        int last = first + n - 1;                        // offset of the element whose reaction this lane holds
+        if (p == 0) {
+            float ux, uy;
+            pair_sym<false, PRECISE>(tl[16], tgA, kp, aAx, aAy, ux, uy);
+        } else if (p == 1) {
+            bx = __shfl_sync(kFull, bx, nxt);
+            by = __shfl_sync(kFull, by, nxt);
+            const float4 q = tl[16];
+            float ux, uy;
+            pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
+            pair_sym<false, PRECISE>(q, tgB, kp, aBx, aBy, ux, uy);
+            last = 16;
         }
+        sm.slot[(H * nslots + o) * 32 + ((lane + last) & 31)] = make_float2(bx, by);
     }
     vx[0] = aAx; vy[0] = aAy; vx[1] = aBx; vy[1] = aBy;
 }
@@ -512,7 +522,7 @@ __device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const
     return -tot / (double)kp.N;
 }
 
-// SwarmEnv._step on the stage buffer sm.st.  Preconditions: st.xs/nx/as/an and sm.act filled, each
+// SwarmEnv._step on the stage buffer sm.st.  Preconditions: st.xs/as/an, sm.nx and sm.act filled, each
 // element written by the thread that owns it here (element i <-> thread i mod n) or visible through
 // a barrier.  Postcondition: state updated and visible to the whole group; returns the reward.
 template <int MODE, bool PRECISE>
@@ -534,6 +544,7 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
     float vx[T], vy[T];
     const double e = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
     energy_put(sm, g, e);
+    cp_async_wait_but_one();   // this thread's own noise rows have landed in sm.nx (no-op outside k_step)
     // multiagent.py:40  locusts move with the pre-cutoff v just computed
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -541,7 +552,7 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
         if (j < kp.N) {
             if (v_out) reinterpret_cast<float2*>(v_out)[j] = make_float2(vx[t], vy[t]);
             double2 p = sm.st.xs[j];
-            move_particle(p, make_double2((double)vx[t], (double)vy[t]), sm.st.nx[j], kp.dt, kp.sigma);
+            move_particle(p, make_double2((double)vx[t], (double)vy[t]), sm.nx[j], kp.dt, kp.sigma);
             sm.st.xs[j] = p;
         }
     }
@@ -549,47 +560,61 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
     return energy_get(sm, kp, g);
 }
 
-// SwarmEnv._reset (multiagent.py:46-63) for env e on the stage buffer: draws (injected or Philox),
-// n_burn burn-in steps with noise row k, then the frozen row n_burn is stored for all later
-// steps (Q1).  Ends with the state visible to the whole group.
-template <int MODE, bool PRECISE>
-__device__ __forceinline__ void env_reset(const Smem& sm, const KP& kp, const Grp& g, int e, uint32_t episode,
-                                          const bool inj, const SwarmInjectedDraws& dr, const SwarmState& st) {
+// SwarmEnv._reset (multiagent.py:46-63) for env e on the stage buffer, in two pieces so that the
+// burn-in steps can share the ONE env_step call site of the calling kernel:
+//   reset_begin      the initial positions (injected or Philox draws)
+//   reset_row(r)     noise row r and burn-in action r into the stage buffer; for r == n_burn the row is
+//                    the frozen one: it is stored to HBM for all later steps and the
+//                    function returns true (no step follows).
+// Sequence: reset_begin; for (r = 0; !reset_row(r); ++r) env_step.
+struct ResetCtx {
+    DrawCtx draw;
+    int e;
+    bool inj;
+};
+
+__device__ __forceinline__ ResetCtx reset_begin(const Smem& sm, const KP& kp, const Grp& g, int e, uint32_t episode,
+                                                const bool inj, const SwarmInjectedDraws& dr) {
     const int N = kp.N, A = kp.A;
-    DrawCtx ctx;
-    ctx.key = kp.key;
-    ctx.env = kp.env_off + (uint32_t)e;
-    ctx.episode = episode;
-    g.sync();      // the previous step's readers of red / src are done
+    ResetCtx rc;
+    rc.draw.key = kp.key;
+    rc.draw.env = kp.env_off + (uint32_t)e;
+    rc.draw.episode = episode;
+    rc.e = e;
+    rc.inj = inj;
+    g.sync();      // the previous step's readers of red / src / xs are done
     for (int i = g.tid; i < N; i += g.n)
         sm.st.xs[i] = inj ? reinterpret_cast<const double2*>(dr.x0)[(size_t)e * N + i]
-                          : draw_uniform2(ctx, STREAM_X0, i);
+                          : draw_uniform2(rc.draw, STREAM_X0, i);
     for (int k = g.tid; k < A; k += g.n)
         sm.st.as[k] = inj ? reinterpret_cast<const double2*>(dr.xa0)[(size_t)e * A + k]
-                          : draw_uniform2(ctx, STREAM_XA0, k);
-    const int rows = kp.n_burn + 1;
-    for (int r = 0; r <= kp.n_burn; ++r) {
-        for (int j = g.tid; j < N; j += g.n) {
-            const double2 z = inj ? reinterpret_cast<const double2*>(dr.particle_noise)[((size_t)e * rows + r) * N + j]
-                                  : draw_normal2(ctx, STREAM_NOISE_X, r, j);
-            sm.st.nx[j] = z;
-            if (r == kp.n_burn) reinterpret_cast<double2*>(st.noise_x)[(size_t)e * N + j] = z;   // frozen row -> HBM
-        }
-        for (int k = g.tid; k < A; k += g.n) {
-            const double2 z = inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
-                                  : draw_normal2(ctx, STREAM_NOISE_A, r, k);
-            sm.st.an[k] = z;
-            if (r == kp.n_burn) {
-                reinterpret_cast<double2*>(st.noise_a)[(size_t)e * A + k] = z;
-            } else {
-                sm.act[k] = inj ? reinterpret_cast<const double2*>(dr.burn_actions)[((size_t)e * kp.n_burn + r) * A + k]
-                                : draw_normal2(ctx, STREAM_BURN, r, k);
-            }
-        }
-        if (r == kp.n_burn) break;
-        env_step<MODE, PRECISE>(sm, kp, g, nullptr);
+                          : draw_uniform2(rc.draw, STREAM_XA0, k);
+    return rc;
+}
+
+__device__ __forceinline__ bool reset_row(const Smem& sm, const KP& kp, const Grp& g, const ResetCtx& rc, const int r,
+                                          const SwarmInjectedDraws& dr, const SwarmState& st) {
+    const int N = kp.N, A = kp.A, e = rc.e, rows = kp.n_burn + 1;
+    const bool last = r >= kp.n_burn;
+    for (int j = g.tid; j < N; j += g.n) {
+        const double2 z = rc.inj ? reinterpret_cast<const double2*>(dr.particle_noise)[((size_t)e * rows + r) * N + j]
+                                 : draw_normal2(rc.draw, STREAM_NOISE_X, r, j);
+        sm.nx[j] = z;
+        if (last) reinterpret_cast<double2*>(st.noise_x)[(size_t)e * N + j] = z;
     }
-    g.sync();
+    for (int k = g.tid; k < A; k += g.n) {
+        const double2 z = rc.inj ? reinterpret_cast<const double2*>(dr.agent_noise)[((size_t)e * rows + r) * A + k]
+                                 : draw_normal2(rc.draw, STREAM_NOISE_A, r, k);
+        sm.st.an[k] = z;
+        if (last) {
+            reinterpret_cast<double2*>(st.noise_a)[(size_t)e * A + k] = z;
+        } else {
+            sm.act[k] = rc.inj ? reinterpret_cast<const double2*>(dr.burn_actions)[((size_t)e * kp.n_burn + r) * A + k]
+                               : draw_normal2(rc.draw, STREAM_BURN, r, k);
+        }
+    }
+    if (last) g.sync();
+    return last;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -621,18 +646,56 @@ __device__ __forceinline__ void raster_zero_fill(float* __restrict__ grid_e, int
     }
 }
 
+// The same zero fill by the TMA engine (cp.async.bulk shared -> global): the source of the zeros is
+// the rasteriser's own counter table, which is all zero between two envs (env_raster cleans it),
+// so a whole 56 KB observation costs ONE thread a handful of instructions and no LSU traffic.
+// Usable when the table size is a multiple of 16 bytes (cells % 4 == 0) and grid_e is 16-byte
+// aligned.  Protocol (one thread issues, see k_step):
+//   tma_zero_fill_issue    after a barrier that follows the table clean-up
+//   tma_zero_fill_wait_read  before the first atomic on the table (the engine has read its zeros)
+//   tma_zero_fill_wait_done  before the first ordinary store to grid_e (the zeros have landed)
+__device__ __forceinline__ bool tma_zero_fill_ok(const void* grid, int cells) {
+    return (cells & 7) == 0 && (reinterpret_cast<uintptr_t>(grid) & 15) == 0;
+}
+// table_bytes: size of the (all-zero) counter table, a multiple of 16 that divides the grid's 8*cells bytes
+__device__ __forceinline__ void tma_zero_fill_issue(float* __restrict__ grid_e, const uint32_t* table, int cells,
+                                                    uint32_t table_bytes) {
+    // make the generic-proxy zeros of the table visible to the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(table);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(grid_e);
+    const uint32_t total = (uint32_t)cells * 8u;
+    for (uint32_t off = 0; off < total; off += table_bytes)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src),
+                     "r"(table_bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_zero_fill_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_zero_fill_wait_done() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");         // async-proxy writes before the generic stores that follow
+}
+
 // One-time clear of the counter table (afterwards env_raster leaves it clean).
-__device__ __forceinline__ void raster_table_clear(const Smem& sm, int cells, const RGrp& g) {
-    for (int i = g.tid; i < cells; i += g.n) sm.table[i] = 0u;
+__device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, const RGrp& g) {
+    for (int i = g.tid; i < words; i += g.n) sm.table[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA zero fill reads these zeros
 }
 
 // SwarmStateProcessor.process_state (state_processors.py:25-42) of the points pts = [N locusts; A
 // agents] in shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
 // Preconditions: grid_e zero-filled by this group (raster_zero_fill), sm.table all zero and pts
 // visible (a barrier since).  Postcondition: sm.table all zero again, after a group barrier.
+// tma: the zero fill was issued with tma_zero_fill_issue by thread 0 of g (which then also waits).
+// early_release_fn() is called by every thread once it has read its last point from pts (the step
+// kernel hands the buffer back to the force group there).
+struct NoRelease { __device__ __forceinline__ void operator()() const {} };
+template <typename Release>
 __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const RGrp& g,
-                                           float* __restrict__ grid_e, uint8_t* __restrict__ pos_e) {
+                                           float* __restrict__ grid_e, uint8_t* __restrict__ pos_e, const bool tma,
+                                           const Release early_release_fn) {
     const int N = kp.N, A = kp.A, G = kp.G, P = N + A;
+    const bool t16 = table_is16(N, A);
     // phase 0: one thread walks the sequential FP64 mean (np.mean(vstack([x,xa]),axis=0)[0] is a
     // plain left-to-right sum, ~23 cycles per dependent DADD)
     if (g.tid == 0) {
@@ -640,6 +703,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
 #pragma unroll 8
         for (int i = 0; i < P; ++i) s = __dadd_rn(s, pts[i].x);
         sm.box[0] = s / (double)P;
+        if (tma) tma_zero_fill_wait_read();      // the table may be written from here on
     }
     g.sync();
     // phase 1: bin every point in FP64 against numpy's edges, count with warp-aggregated atomics
@@ -672,24 +736,42 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
         const uint32_t peers = __match_any_sync(kFull, key);
         int mine = -1;
         if (key != 0xffffffffu && (__ffs(peers) - 1) == (g.tid & 31)) {
-            const uint32_t inc = (uint32_t)__popc(peers) << ((key & 1u) ? 16 : 0);
-            const uint32_t old = atomicAdd(&sm.table[cell], inc);
-            if (old == 0u) mine = cell;               // first arrival writes the cell out
+            const uint32_t cnt = (uint32_t)__popc(peers);
+            if (t16) {   // 16 bits per cell, two cells per word
+                const int sh = (cell & 1) << 4;
+                const uint32_t old = atomicAdd(&sm.table[cell >> 1], (cnt << ((key & 1u) ? kAgentShift : 0)) << sh);
+                if (((old >> sh) & 0xffffu) == 0u) mine = cell;   // first arrival writes the cell out
+            } else {
+                const uint32_t old = atomicAdd(&sm.table[cell], cnt << ((key & 1u) ? 16 : 0));
+                if (old == 0u) mine = cell;
+            }
         }
         if (p < P) sm.cid[p] = mine;
     }
+    early_release_fn();
+    if (tma && g.tid == 0) tma_zero_fill_wait_done();   // the zeros are in place before anyone scatters over them
     g.sync();
     // phase 2: sparse scatter of the non-zero cells over the zero fill; the writer cleans its counter
     float2* g2 = reinterpret_cast<float2*>(grid_e);
     for (int p = g.tid; p < P; p += g.n) {
         const int c = sm.cid[p];
         if (c >= 0) {
-            const uint32_t w = sm.table[c];
-            sm.table[c] = 0u;
-            g2[c] = make_float2(__fdiv_rn((float)(w & 0xffffu), (float)N),
-                                A > 0 ? __fdiv_rn((float)(w >> 16), (float)A) : 0.f);
+            uint32_t nl, na;
+            if (t16) {
+                const int sh = (c & 1) << 4;
+                const uint32_t w = (atomicAnd(&sm.table[c >> 1], ~(0xffffu << sh)) >> sh) & 0xffffu;
+                nl = w & ((1u << kAgentShift) - 1u);
+                na = w >> kAgentShift;
+            } else {
+                const uint32_t w = sm.table[c];
+                sm.table[c] = 0u;
+                nl = w & 0xffffu;
+                na = w >> 16;
+            }
+            g2[c] = make_float2(__fdiv_rn((float)nl, (float)N), A > 0 ? __fdiv_rn((float)na, (float)A) : 0.f);
         }
     }
+    if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cleaned counters -> next TMA zero fill
     g.sync();
 }
 

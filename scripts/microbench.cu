@@ -41,6 +41,26 @@ __global__ void k_pipe(float* out, float seed) {
     if (s == 123.456f) out[0] = s;
 }
 
+template <int OP>
+__global__ void k_pipe64(double* out, double seed) {
+    double v[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) v[c] = seed + 0.001 * (threadIdx.x + c);
+    for (int i = 0; i < ITERS / 8; ++i) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            if (OP == 0) v[c] = __dadd_rn(v[c], seed);
+            if (OP == 1) v[c] = __fma_rn(v[c], seed, seed);
+            if (OP == 2) v[c] = (double)(float)v[c] + 0.0;        // F2F.F32.F64 + F2F.F64.F32
+            if (OP == 3) v[c] = (double)(int)v[c];                // F2I + I2F
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += v[c];
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void k_dadd_latency(double* out, long long* cyc, double seed) {
     double s = seed;
     long long t0 = clock64();
@@ -107,6 +127,25 @@ int main() {
         const double per_s = ops / (ms * 1e-3);
         printf("{\"bench\": \"%s\", \"ms\": %.4f, \"thread_ops_per_s\": %.4e, \"per_clk_per_sm_at_1965MHz\": %.2f}\n",
                names[op], ms, per_s, per_s / sms / 1.965e9);
+    }
+    {
+        double* d;
+        CK(cudaMalloc(&d, 1024));
+        const char* n64[] = {"dadd", "dfma", "cvt_f64_f32_roundtrip", "cvt_f64_i32_roundtrip"};
+        for (int op = 0; op < 4; ++op) {
+            const int blocks = sms * 8, threads = 256;
+            float ms = 0;
+            switch (op) {
+                case 0: ms = time_ms([&] { k_pipe64<0><<<blocks, threads>>>(d, 0.5); }); break;
+                case 1: ms = time_ms([&] { k_pipe64<1><<<blocks, threads>>>(d, 0.5); }); break;
+                case 2: ms = time_ms([&] { k_pipe64<2><<<blocks, threads>>>(d, 0.5); }); break;
+                case 3: ms = time_ms([&] { k_pipe64<3><<<blocks, threads>>>(d, 0.5); }); break;
+            }
+            const double ops = (double)blocks * threads * (ITERS / 8) * CHAINS;
+            const double per_s = ops / (ms * 1e-3);
+            printf("{\"bench\": \"%s\", \"ms\": %.4f, \"thread_ops_per_s\": %.4e, \"per_clk_per_sm_at_1965MHz\": %.2f}\n",
+                   n64[op], ms, per_s, per_s / sms / 1.965e9);
+        }
     }
     {
         double* d; long long* c;
