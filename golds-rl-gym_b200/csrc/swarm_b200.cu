@@ -156,10 +156,9 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                 oa[k] = q;
                 if (raster) rx[N + k] = q;
             }
-            if (raster) {
-                __threadfence_block();
-                bar_arrive<BAR_FULL>(n_all);
-            }
+            // bar.arrive / bar.sync order the shared-memory writes above for the threads that complete
+            // the barrier (PTX ISA, producer/consumer example of barrier.arrive): no extra fence
+            if (raster) bar_arrive<BAR_FULL>(n_all);
         }
     } else {
         const RGrp g = {(int)threadIdx.x - n_force, n_raster};
@@ -174,18 +173,14 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             // The observation is ~99 % zeros: stream them out while the force group still computes
             // (TMA bulk stores fed from the clean counter table, else plain stores); the non-zero cells
             // are scattered over them afterwards.
-            const bool xp_nozf = io.flags & 256u, xp_noraster = io.flags & 512u;   // EXPERIMENT
-            if (!xp_nozf) {
             if (tma) {
                 if (g.tid == 0) tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
             } else {
                 raster_zero_fill(grid_e, cells, g.tid, g.n);
             }
-            }
             bar_sync<BAR_FULL>(n_all);
             auto release = [more, n_all]() { if (more) bar_arrive<BAR_EMPTY>(n_all); };
-            if (!xp_noraster) env_raster(sm, sm.rx, kp, g, grid_e, io.positions + (size_t)e * A * 2, tma && !xp_nozf, release);
-            else release();
+            env_raster(sm, sm.rx, kp, g, grid_e, io.positions + (size_t)e * A * 2, tma, release);
         }
     }
 }
@@ -375,7 +370,7 @@ int block_threads(int N) {
 }
 
 // threads of the raster group riding along with the force group in k_step
-int raster_threads(int N, int A) { return (N + A) <= 128 ? 32 : 64; }
+int raster_threads(int N, int A) { return (N + A) <= 128 ? 32 : ((N + A) <= 1024 ? 64 : 128); }
 
 size_t step_smem(const SwarmParams* p, bool raster, int n_stage = 2) {
     return smem_bytes(p->n_locusts, p->n_agents, p->grid_size, n_stage, true, raster, force_sym(force_mode(p->n_locusts)));
@@ -544,12 +539,11 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (!io->reward || !io->done) return SWARM_ERR_NULL;
     if ((io->flags & SWARM_STEP_ACTIONS_F64) ? !io->actions_f64 : !io->actions_f32) return SWARM_ERR_NULL;
     if ((io->grid != nullptr) != (io->positions != nullptr)) return SWARM_ERR_FLAGS;
-    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64 | 768u)) return SWARM_ERR_FLAGS;
+    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
     if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
     const bool raster = io->grid != nullptr;
-    size_t smem = step_smem(p, raster);
-    if (const char* pad = getenv("SWARM_EXP_PAD_SMEM")) smem += (size_t)atoi(pad);   // occupancy experiments only
+    const size_t smem = step_smem(p, raster);
     const int nf = block_threads(kp.N);
     const int nt = nf + (raster ? raster_threads(kp.N, kp.A) : 0);
     const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;

@@ -367,18 +367,126 @@ __device__ __forceinline__ void pair_sym(const float4 q, const float4 tg, const 
     }
 }
 
+// ---- packed FP32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot, two FP32 results ------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Two targets of one lane, negated and split like the sources: d = (q.hi + nh) + (q.lo + nl).
+struct Targets2 {
+    f32x2 nhA, nlA, nhB, nlB;
+};
+__device__ __forceinline__ Targets2 make_targets2(const float4 tgA, const float4 tgB) {
+    Targets2 t;
+    t.nhA = pk2(-tgA.x, -tgA.y); t.nlA = pk2(-tgA.z, -tgA.w);
+    t.nhB = pk2(-tgB.x, -tgB.y); t.nlB = pk2(-tgB.z, -tgB.w);
+    return t;
+}
+struct PairConst2 {
+    f32x2 nInvL2, nF2, eps2;
+};
+__device__ __forceinline__ PairConst2 make_pair_const2(const KP& kp) {
+    PairConst2 c;
+    c.nInvL2 = pk2(kp.nInvL, kp.nInvL);
+    c.nF2 = pk2(-kp.F, -kp.F);
+    c.eps2 = pk2(kp.eps_s, kp.eps_s);
+    return c;
+}
+
+// One source q against both targets of the lane, fast math.  The geometry is packed by component
+// (x,y), the scalar chain r -> w by target (A,B); MUFU stays scalar.  Accumulates the NEGATED
+// forces: naX += -w_X d_X (X = A, B) and, with REACT, the reaction b += -(w_A d_A + w_B d_B).
+// Operation for operation the same roundings as pair_sym<.., false> (negation is exact).
+template <bool REACT>
+__device__ __forceinline__ void pair2_fast(const float4 q, const Targets2& t, const PairConst2& c, f32x2& naA, f32x2& naB,
+                                           f32x2& b) {
+    const f32x2 qh = pk2(q.x, q.y), ql = pk2(q.z, q.w);
+    const f32x2 dA = add2(add2(qh, t.nhA), add2(ql, t.nlA));
+    const f32x2 dB = add2(add2(qh, t.nhB), add2(ql, t.nlB));
+    float dAx, dAy, dBx, dBy;
+    upk2(dA, dAx, dAy);
+    upk2(dB, dBx, dBy);
+    // r2 >= 1e-30 keeps rsqrt finite for coincident points (their d is 0 anyway)
+    const float r2A = fmaf(dAx, dAx, fmaf(dAy, dAy, 1e-30f));
+    const float r2B = fmaf(dBx, dBx, fmaf(dBy, dBy, 1e-30f));
+    float riA, riB;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(riA) : "f"(r2A));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(riB) : "f"(r2B));
+    const f32x2 r = mul2(pk2(r2A, r2B), pk2(riA, riB));
+    const f32x2 arg = mul2(r, c.nInvL2);
+    const f32x2 rpe = add2(r, c.eps2);
+    float rA, rB, gA, gB, pA, pB;
+    upk2(r, rA, rB);
+    upk2(arg, gA, gB);
+    upk2(rpe, pA, pB);
+    float e1A, e1B, e2A, e2B, iA, iB;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1A) : "f"(-rA));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1B) : "f"(-rB));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2A) : "f"(gA));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2B) : "f"(gB));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(pA));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iB) : "f"(pB));
+    const f32x2 ns = fma2(c.nF2, pk2(e2A, e2B), pk2(e1A, e1B));      // -(F e2 - e1)
+    const f32x2 nw = mul2(ns, pk2(iA, iB));                          // (-w_A, -w_B)
+    float nwA, nwB;
+    upk2(nw, nwA, nwB);
+    const f32x2 nwA2 = pk2(nwA, nwA), nwB2 = pk2(nwB, nwB);
+    naA = fma2(nwA2, dA, naA);
+    naB = fma2(nwB2, dB, naB);
+    if (REACT) {
+        b = fma2(nwA2, dA, b);
+        b = fma2(nwB2, dB, b);
+    }
+}
+
 // n rotation steps of one half-tile pass with both targets (see tile_sym for the conventions).
 template <bool PRECISE>
 __device__ __forceinline__ void tile_sym2(const float4* __restrict__ tl, const int n, const float4 tgA, const float4 tgB,
                                           const KP& kp, const int nxt, float& aAx, float& aAy, float& aBx, float& aBy,
                                           float& bx, float& by) {
+    if constexpr (PRECISE) {
 #pragma unroll kTileUnroll
-    for (int k = 0; k < n; ++k) {
-        bx = __shfl_sync(kFull, bx, nxt);
-        by = __shfl_sync(kFull, by, nxt);
-        const float4 q = tl[k];
-        pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
-        pair_sym<true, PRECISE>(q, tgB, kp, aBx, aBy, bx, by);
+        for (int k = 0; k < n; ++k) {
+            bx = __shfl_sync(kFull, bx, nxt);
+            by = __shfl_sync(kFull, by, nxt);
+            const float4 q = tl[k];
+            pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
+            pair_sym<true, PRECISE>(q, tgB, kp, aBx, aBy, bx, by);
+        }
+    } else {
+        const Targets2 t = make_targets2(tgA, tgB);
+        const PairConst2 c = make_pair_const2(kp);
+        f32x2 naA = pk2(-aAx, -aAy), naB = pk2(-aBx, -aBy);
+#pragma unroll kTileUnroll
+        for (int k = 0; k < n; ++k) {
+            bx = __shfl_sync(kFull, bx, nxt);
+            by = __shfl_sync(kFull, by, nxt);
+            f32x2 b = pk2(bx, by);
+            pair2_fast<true>(tl[k], t, c, naA, naB, b);
+            upk2(b, bx, by);
+        }
+        upk2(naA, aAx, aAy);
+        upk2(naB, aBx, aBy);
+        aAx = -aAx; aAy = -aAy; aBx = -aBx; aBy = -aBy;
     }
 }
 
@@ -454,10 +562,21 @@ __device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp
     }
     const float4 tgA = sm.src[(2 * I) * 64 + lane], tgB = sm.src[(2 * I + 1) * 64 + lane];
     const float4* ag = sm.src + nt2 * 128;      // agents act on locusts only (multiagent.py:108-113)
-    for (int k = 0; k < kp.A; ++k) {
-        const float4 q = ag[k];
-        pair_ordered<PRECISE>(q, tgA, kp, vx[0], vy[0]);
-        pair_ordered<PRECISE>(q, tgB, kp, vx[1], vy[1]);
+    if constexpr (PRECISE) {
+        for (int k = 0; k < kp.A; ++k) {
+            const float4 q = ag[k];
+            pair_ordered<PRECISE>(q, tgA, kp, vx[0], vy[0]);
+            pair_ordered<PRECISE>(q, tgB, kp, vx[1], vy[1]);
+        }
+    } else {
+        const Targets2 t = make_targets2(tgA, tgB);
+        const PairConst2 c = make_pair_const2(kp);
+        f32x2 naA = pk2(-vx[0], -vy[0]), naB = pk2(-vx[1], -vy[1]), b = 0;
+#pragma unroll 2
+        for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
+        upk2(naA, vx[0], vy[0]);
+        upk2(naB, vx[1], vy[1]);
+        vx[0] = -vx[0]; vy[0] = -vy[0]; vx[1] = -vx[1]; vy[1] = -vy[1];
     }
 }
 

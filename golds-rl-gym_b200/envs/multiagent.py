@@ -152,7 +152,7 @@ class BatchedSwarmEnv(object):
         else:
             io.grid, io.positions = None, None
         io.v_out = v_out.data_ptr() if v_out is not None else None
-        io.flags = flags | int(__import__('os').environ.get('SWARM_XP_FLAGS', '0'))
+        io.flags = flags
         rc = self.lib.swarm_step(self._params_ref, self._state_ref, self._io_ref,
                                  ctypes.byref(reset_draws.c) if reset_draws is not None else None,
                                  torch.cuda.current_stream(self.device).cuda_stream)

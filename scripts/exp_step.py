@@ -17,8 +17,5 @@ def run(E, N, raster, steps=100):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps * 1e3
 
-if os.environ.get("SWARM_EXP_PAD_SMEM"):
-    print("pad", os.environ["SWARM_EXP_PAD_SMEM"], "4096x256 no raster: %.1f us" % run(4096, 256, False))
-else:
-    for E, N in [(4096, 256), (4096, 64)]:
-        print(os.environ.get("SWARM_XP_FLAGS"), E, N, "raster: %.1f us   no raster: %.1f us" % (run(E, N, True), run(E, N, False)))
+for E, N in [(4096, 256), (1024, 64), (4096, 64), (4096, 80), (32, 80), (1024, 512), (256, 1024), (64, 2048)]:
+    print(E, N, "raster: %.1f us   no raster: %.1f us" % (run(E, N, True), run(E, N, False)))

@@ -41,6 +41,30 @@ __global__ void k_pipe(float* out, float seed) {
     if (s == 123.456f) out[0] = s;
 }
 
+// packed FP32 pairs (sm_100+): one issue slot, two FP32 results
+template <int OP>
+__global__ void k_pipe2(float* out, float seed) {
+    unsigned long long v[CHAINS], sd;
+    float2 s2 = make_float2(seed, seed * 0.5f);
+    sd = *reinterpret_cast<unsigned long long*>(&s2);
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) {
+        float2 t = make_float2(seed + 0.001f * (threadIdx.x + c), seed);
+        v[c] = *reinterpret_cast<unsigned long long*>(&t);
+    }
+    for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            if (OP == 0) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(v[c]) : "l"(sd));
+            if (OP == 1) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(v[c]) : "l"(sd));
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) { float2 t = *reinterpret_cast<float2*>(&v[c]); s += t.x + t.y; }
+    if (s == 123.456f) out[0] = s;
+}
+
 template <int OP>
 __global__ void k_pipe64(double* out, double seed) {
     double v[CHAINS];
@@ -127,6 +151,15 @@ int main() {
         const double per_s = ops / (ms * 1e-3);
         printf("{\"bench\": \"%s\", \"ms\": %.4f, \"thread_ops_per_s\": %.4e, \"per_clk_per_sm_at_1965MHz\": %.2f}\n",
                names[op], ms, per_s, per_s / sms / 1.965e9);
+    }
+    {
+        const int blocks = sms * 8, threads = 256;
+        float ms = time_ms([&] { k_pipe2<0><<<blocks, threads>>>(out, 0.5f); });
+        double per_s = (double)blocks * threads * ITERS * CHAINS / (ms * 1e-3);
+        printf("{\"bench\": \"ffma2\", \"ms\": %.4f, \"thread_inst_per_s\": %.4e, \"inst_per_clk_per_sm_at_1965MHz\": %.2f}\n", ms, per_s, per_s / sms / 1.965e9);
+        ms = time_ms([&] { k_pipe2<1><<<blocks, threads>>>(out, 0.5f); });
+        per_s = (double)blocks * threads * ITERS * CHAINS / (ms * 1e-3);
+        printf("{\"bench\": \"fadd2\", \"ms\": %.4f, \"thread_inst_per_s\": %.4e, \"inst_per_clk_per_sm_at_1965MHz\": %.2f}\n", ms, per_s, per_s / sms / 1.965e9);
     }
     {
         double* d;
