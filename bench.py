@@ -31,6 +31,23 @@ A, G = 10, 84
 FLOPS_PER_PAIR = 18
 
 
+def ncu_traffic(kernel="k_step"):
+    """dram read+write bytes per launch of the dominant kernel, from the committed ncu --set full summary."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for name in sorted(os.listdir(pdir)):
+            if name.endswith("_summary.json"):
+                with open(os.path.join(pdir, name)) as f:
+                    d = json.load(f).get(kernel, {})
+                if "dram__bytes_read.sum" in d:
+                    unit = 1e6      # ncu prints Mbyte for this kernel
+                    best = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * unit
+    except Exception:
+        pass
+    return best
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -117,6 +134,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--math", default="fast", choices=["fast", "precise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU-baseline sample")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.warmup < 3:
@@ -173,9 +192,28 @@ def main():
     step = lambda i: env.step(ring[i & 7])
     for i in range(W):
         step(i)
+    # The device-resident rollout replays a CUDA graph of 8 consecutive steps (one per action tensor of
+    # the ring): same kernels, same arguments, no per-step host work.  K is rounded up to a multiple of 8.
+    graph = None
+    if not args.no_graph:
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(8):
+                step(i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(8):
+                step(i)
+        K = ((K + 7) // 8) * 8
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
-    ms = timed(step, K)
+    if graph is not None:
+        ms = timed(lambda i: graph.replay(), K // 8)
+    else:
+        ms = timed(step, K)
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if sampler else None
 
@@ -223,7 +261,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline as cb
-        steps_cpu = 20 if N >= 200 else 100
+        probe = cb.time_port(N, steps=4, warmup=1, envs_per_proc=2)
+        steps_cpu = int(max(8, min(20000, args.cpu_seconds * probe["steps"] / max(probe["seconds"], 1e-6))))
         res = cb.time_port(N, steps=steps_cpu, warmup=1, envs_per_proc=2)
         cpu = {"value": res["env_steps_per_s"] * N, "unit": "locust-updates/s", "cores": res["procs"], "kind": "port",
                "sample": "%d envs (2 per core) x %d steps, NumPy FP64 port of SwarmEnv.step + process_state, "
@@ -238,13 +277,22 @@ def main():
             "config": {"workload": wl["name"] + "; fused step + TimeLimit(128) + auto-reset + 84x84 compact rasterise",
                        "envs_per_gpu": E, "n_locusts": N, "n_agents": A, "grid": G, "math": args.math,
                        "actions": "N(0,1) clipped to unit norm, 8 pre-generated device tensors",
+                       "launch": "python per step" if args.no_graph else "CUDA graph of 8 steps replayed",
                        "l2": "no explicit flush: each step streams %.0f MB of observations (> 126 MB L2 for c4)"
                              % (E * G * G * 2 * 4 / 1e6),
                        "parallelism": "env-sharded x%d, no collective" % world},
             "env_steps_per_sec": env_steps, "pairs_per_sec": env_steps * N * (N + A),
-            "roofline": {"bound": "fp32", "kernel": "k_step (fused)", "achieved": achieved, "peak": fp32_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
-                         "note": "algorithmic 18 flop/pair x %d pairs/launch; peak = 148 SM x 128 lanes x 2 x %.0f MHz (%s clock)"
+            "roofline": {"bound": "fp32", "kernel": "k_step (fused step + rasterise)", "achieved": achieved, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "traffic": ncu_traffic() if args.workload == "c4" else None,
+                         "xu_pipe": {"achieved_mufu_per_s": 2.0 * pairs_per_launch / (ms / K * 1e-3),
+                                     "peak_mufu_per_s": 148 * 15.93 * pk["sm_max_mhz"] * 1e6,
+                                     "frac": 2.0 * pairs_per_launch / (ms / K * 1e-3) / (148 * 15.93 * pk["sm_max_mhz"] * 1e6),
+                                     "note": "the saturated pipe: 4 MUFU per UNORDERED pair = 2 per ordered pair; "
+                                             "15.93 MUFU/clk/SM measured (scripts/microbench.cu)"},
+                         "note": "compute-bound kernel (190 flop/B): algorithmic 18 flop/pair x %d ordered pairs/launch over the "
+                                 "mean launch duration of the timed region; peak = 148 SM x 128 lanes x 2 x %.0f MHz (%s clock); "
+                                 "traffic = ncu dram read+write bytes per launch (profiles/)"
                                  % (pairs_per_launch, pk["sm_max_mhz"], pk["source"])},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": hbm / pk["hbm_gbs"], "bytes_per_launch": E * bytes_per_env, "peak_source": pk["source"]},
