@@ -27,6 +27,11 @@ WORKLOADS = {
     # BASELINE.json configs[1]
     "c2": dict(E=1024, N=64, name="C2 batched swarm env: 1024 envs x 64 locusts per GPU"),
 }
+PAAC = {
+    # BASELINE.json configs[2] / configs[4]
+    "paac3": dict(E=32, name="C3 PAAC conv training as in scripts/train_paac_conv.py (--height=84 --clip_norm=1), 32 emulators"),
+    "paac5": dict(E=1024, name="C5 PAAC conv training, 1024 emulators per GPU (8192 over 8 GPUs), NCCL gradient all-reduce"),
+}
 A, G = 10, 84
 FLOPS_PER_PAIR = 18
 
@@ -125,18 +130,75 @@ def run_reference(args, wl):
     }))
 
 
+def paac_frames_per_sec(E_per_gpu, updates, warmup_updates, world, rank, local):
+    """PAAC frames/s (= T*E / loop time, paac.py:397-401) of the device-resident learner, CUDA-event timed."""
+    import torch
+    import golds_rl_gym_b200 as pkg
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import train_paac_conv as tp
+    args = tp.get_arg_parser().parse_args(["--height=84", "--clip_norm=1", "-ec", str(E_per_gpu * world)])
+    net_creator, env_creator = tp.get_network_and_environment_creator(args)
+    learner = pkg.submodule("agents.paac.paac").GridPAACLearner(net_creator, env_creator, args)
+    learner.runners.start(states_out=learner.states[0])
+    for _ in range(warmup_updates):
+        learner.update()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(updates):
+        learner.update()
+    e1.record()
+    torch.cuda.synchronize()
+    sh = pkg.submodule("sharding")
+    ms = sh.max_over_ranks(e0.elapsed_time(e1), device=torch.device("cuda", local))
+    frames = updates * learner.max_local_steps * learner.total_emulators
+    return dict(frames_per_sec=frames / (ms * 1e-3), ms_per_update=ms / updates, updates=updates,
+                emulators=learner.total_emulators, local_steps=learner.max_local_steps,
+                policy_batch=learner.real_batch_size, net_dtype="fp32 (cuDNN TF32 convolutions, FP32 dense)",
+                launch="one CUDA graph per update (rollout + returns + backward + all-reduce + Adam)")
+
+
+def run_paac(args, wl):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = paac_frames_per_sec(wl["E"], max(args.steps, 8), max(args.warmup, 3), world, rank, local)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "paac_frames_per_sec", "value": res["frames_per_sec"], "unit": "frames/s", "n_gpus": world,
+            "steps": res["updates"], "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_update"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": res["net_dtype"],
+            "data": "synthetic", "config": {"workload": wl["name"], "emulators_per_gpu": wl["E"], "n_locusts": 80,
+                                            "n_agents": A, "grid": G, "local_steps": res["local_steps"],
+                                            "parallelism": "env-sharded x%d, flat-gradient NCCL all-reduce" % world},
+            "paac": res, "gpu_launches": res["updates"] * res["local_steps"] * 3}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + sorted(PAAC))
     ap.add_argument("--math", default="fast", choices=["fast", "precise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-paac", action="store_true", help="skip the secondary PAAC frames/s figure (config 3)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU-baseline sample")
     args = ap.parse_args()
+    if args.workload in PAAC:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference learner needs TensorFlow 1.4 (not in this image)"}))
+            return
+        return run_paac(args, PAAC[args.workload])
     wl = WORKLOADS[args.workload]
     if args.warmup < 3:
         args.warmup = 3
@@ -269,6 +331,16 @@ def main():
                          "one process per core; %.1f s" % (res["envs"], res["steps"], res["seconds"]),
                "env_steps_per_sec": res["env_steps_per_s"]}
 
+    paac = None
+    if world == 1 and not args.no_paac:
+        try:
+            del env
+            torch.cuda.empty_cache()
+            paac = paac_frames_per_sec(PAAC["paac3"]["E"], 200, 20, 1, 0, local)
+            paac["config"] = PAAC["paac3"]["name"]
+        except Exception as exc:      # the secondary figure must never take the headline down
+            paac = {"error": repr(exc)}
+
     if rank == 0:
         out = {
             "metric": "locust_updates_per_sec", "value": env_steps * N, "unit": "locust-updates/s",
@@ -310,6 +382,8 @@ def main():
         }
         if cpu:
             out["cpu_baseline"] = cpu
+        if paac is not None:
+            out["paac"] = paac
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -38,11 +38,14 @@ class GridRunners(object):
         self.variables = [self.states, self.histories, env.positions, self.rewards, self.episode_over, self.actions]
         self._started = False
 
-    def start(self):
-        """runners.py:34-36.  Initial reset + first observation (paac.py:247-251 does this in the parent)."""
+    def start(self, states_out=None):
+        """runners.py:34-36.  Initial reset + first observation (paac.py:247-251 does this in the parent).
+        states_out: optional (E,A,G,G,3) tensor that receives the expanded observation instead of self.states."""
         self.env.reset()
         self.env.observe()
-        if self.expand:
+        if states_out is not None:
+            self.env.local_states(out=states_out)
+        elif self.expand:
             self.env.local_states(out=self.states)
         self._started = True
 
@@ -52,13 +55,17 @@ class GridRunners(object):
     def get_shared_variables(self):
         return self.variables
 
-    def update_environments(self):
+    def update_environments(self, states_out=None):
+        """states_out: optional (E,A,G,G,3) tensor that receives the new expanded observation directly (the
+        device-resident learner points it at its rollout ring, saving one 847 KB/env copy per step)."""
         if self.coord is not None and self.coord.should_stop():
             self.stop()
             return
         env = self.env
         _, reward, done, _ = env.step(self.actions, rasterize=True, auto_reset=True)
-        if self.expand:
+        if states_out is not None:
+            env.local_states(out=states_out)
+        elif self.expand:
             env.local_states(out=self.states)
         # reward / done scalars broadcast over the agent axis (emulator_runner.py:147-148)
         self.rewards.copy_(reward[:, None].expand_as(self.rewards))

@@ -1,0 +1,74 @@
+"""GPU tests of the device-resident PAAC learner (mirror of fed_gym/agents/paac/paac.py:216-419): the rollout
+contract, the n-step returns, the reference's reward mis-indexing (Q6) vs the fixed mode, CUDA-graph replay."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+
+def make_learner(pkg, cuda, E=4, n_locusts=16, graph=False, **kw):
+    import train_paac_conv as tp
+    args = tp.get_arg_parser().parse_args(["--clip_norm", "1", "-ec", str(E), "--n_locusts", str(n_locusts)])
+    net_creator, env_creator = tp.get_network_and_environment_creator(args)
+    paac = pkg.submodule("agents.paac.paac")
+    return paac.GridPAACLearner(net_creator, env_creator, args, use_cuda_graph=graph, **kw)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_update_runs_and_learns_something(pkg, cuda, graph):
+    L = make_learner(pkg, cuda, graph=graph)
+    L.runners.start(states_out=L.states[0])
+    before = torch.cat([p.detach().flatten().clone() for p in L.network.parameters()])
+    for _ in range(3):
+        L.update()
+    torch.cuda.synchronize()
+    after = torch.cat([p.detach().flatten() for p in L.network.parameters()])
+    assert torch.isfinite(after).all() and not torch.equal(before, after)
+    assert L.global_step == 3 * 5 * 4
+    assert float(L.global_norm) > 0
+    # observation ring: one-hot channel sums to 1 per agent image, grid channels identical across an env's agents
+    s = L.states[0]
+    assert torch.allclose(s[..., 2].sum((-1, -2)), torch.ones_like(s[..., 2].sum((-1, -2))))
+    assert torch.equal(s[:, 0, :, :, :2], s[:, 5, :, :, :2])
+    # clipped actions were stored (paac.py:309,316) and sent to the envs
+    assert (L.actions.norm(dim=-1) <= 1 + 1e-5).all()
+
+
+def test_returns_and_reward_indexing(pkg, cuda):
+    for mode in ("reference", "per_agent"):
+        L = make_learner(pkg, cuda, reward_indexing=mode)
+        L.runners.start(states_out=L.states[0])
+        L._rollout()
+        with torch.no_grad():
+            L._returns()
+        torch.cuda.synchronize()
+        E, A, T = L.emulator_counts, L.N_AGENTS, L.max_local_steps
+        r = L.rewards.cpu().numpy()
+        if mode == "reference":
+            assert (r[:, :E] < 0).all() and (r[:, E:] == 0).all()          # Q6: only the first E columns are written
+        else:
+            assert (r < 0).all() and np.array_equal(r[:, 0], r[:, A - 1])  # env 0's reward on all of its agents
+        obs = L.states[T].view(E * A, *L.states.shape[3:])
+        boot = L.network.predict(obs)["vs"].cpu().numpy()
+        ret = boot.copy()
+        v = L.values.cpu().numpy()
+        for t in reversed(range(T)):
+            ret = r[t] + np.float32(0.99) * ret
+            assert np.allclose(L.y_batch[t].cpu().numpy(), ret, rtol=1e-5, atol=1e-4)
+            assert np.allclose(L.adv_batch[t].cpu().numpy(), ret - v[t], rtol=1e-4, atol=1e-3)
+
+
+def test_lr_annealing_matches_reference_formula(pkg, cuda):
+    L = make_learner(pkg, cuda)
+    L.global_step = 40000000
+    assert abs(L.get_lr() - 0.5e-4) < 1e-12
+    L.global_step = 90000000
+    assert L.get_lr() == 0.0

@@ -38,6 +38,9 @@ def _worker(rank, world, port, total, n_locusts, q):
         allx = sh.gather_shards(torch.as_tensor(x0))
         allnz = sh.gather_shards(torch.as_tensor(nz))
         allids = sh.gather_shards(ids)
+        gflat = torch.full((1000,), float(rank + 1))
+        sh.allreduce_mean_(gflat)
+        assert torch.allclose(gflat, torch.full((1000,), (1 + world) / 2.0))
         slow = sh.max_over_ranks(1.0 + rank)
         tot = sh.sum_over_ranks(float(n))
         if rank == 0:
