@@ -12,6 +12,6 @@ The directory name carries a hyphen (the reference repo's name); import it with
 ``golds_rl_gym_b200``.
 """
 from . import _native
-from ._native import SwarmNativeError, build, load
+from ._native import SwarmNativeError, build, build_torch_ext, load, load_torch_ops
 
-__all__ = ["_native", "SwarmNativeError", "build", "load"]
+__all__ = ["_native", "SwarmNativeError", "build", "build_torch_ext", "load", "load_torch_ops"]

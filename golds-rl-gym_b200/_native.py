@@ -76,7 +76,11 @@ SYMBOLS = {
     "swarm_philox_raw": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
+TORCH_LIB_PATH = os.path.join(_PKG_DIR, "libswarm_b200_torch.so")
+TORCH_SOURCE = os.path.join(_CSRC, "torch_binding.cpp")
+
 _lib = None
+_torch_ops = None
 
 
 class SwarmNativeError(RuntimeError):
@@ -146,3 +150,66 @@ def check(status, what="swarm call"):
         if status == -3:
             msg += ": " + lib.swarm_last_cuda_error().decode()
         raise SwarmNativeError("%s failed (%d): %s" % (what, status, msg))
+
+
+# ------------------------------------------------------------------------------------------------
+# The same C ABI exposed as a PyTorch extension (csrc/torch_binding.cpp -> torch.ops.swarm_b200.*)
+def torch_ext_needs_build():
+    if not os.path.isfile(TORCH_LIB_PATH):
+        return True
+    t = os.path.getmtime(TORCH_LIB_PATH)
+    return any(os.path.isfile(s) and os.path.getmtime(s) > t for s in (TORCH_SOURCE, HEADER))
+
+
+def build_torch_ext(force=False):
+    """g++ csrc/torch_binding.cpp against the installed torch headers/libs and the in-tree libswarm_b200.so."""
+    if not force and not torch_ext_needs_build():
+        return TORCH_LIB_PATH
+    import torch
+    from torch.utils import cpp_extension as ce
+    build()
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise SwarmNativeError("g++ not found; cannot build %s" % TORCH_LIB_PATH)
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    tmp = TORCH_LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ["-I" + p for p in ce.include_paths()] + ["-I" + cuda_inc, TORCH_SOURCE, "-o", tmp]
+    for lp in ce.library_paths():
+        cmd += ["-L" + lp, "-Wl,-rpath," + lp]
+    cmd += ["-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda", "-L" + _PKG_DIR, "-l:libswarm_b200.so",
+            "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise SwarmNativeError("g++ failed:\n%s\n%s" % (res.stdout, res.stderr))
+    os.replace(tmp, TORCH_LIB_PATH)
+    return TORCH_LIB_PATH
+
+
+def load_torch_ops():
+    """-> torch.ops.swarm_b200 (building the extension first if its source is newer and g++ exists)."""
+    global _torch_ops
+    if _torch_ops is not None:
+        return _torch_ops
+    import torch
+    load()                                  # libswarm_b200.so first: the extension links against it
+    if torch_ext_needs_build():
+        try:
+            build_torch_ext()
+        except SwarmNativeError:
+            if not os.path.isfile(TORCH_LIB_PATH):
+                raise
+    torch.ops.load_library(TORCH_LIB_PATH)
+    if int(torch.ops.swarm_b200.abi_version()) != 1:
+        raise SwarmNativeError("torch extension ABI version mismatch")
+    _torch_ops = torch.ops.swarm_b200
+    return _torch_ops
+
+
+def params_blob(params):
+    """The SwarmParams POD as the CPU uint8 tensor the torch ops take."""
+    import torch
+    return torch.frombuffer(bytearray(bytes(params)), dtype=torch.uint8)

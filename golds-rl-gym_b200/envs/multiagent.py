@@ -37,6 +37,9 @@ class InjectedDraws(object):
         self.c = nat.SwarmInjectedDraws(_ptr(self.x0), _ptr(self.xa0), _ptr(self.burn_actions),
                                         _ptr(self.agent_noise), _ptr(self.particle_noise))
 
+    def tensors(self):
+        return [self.x0, self.xa0, self.burn_actions, self.agent_noise, self.particle_noise]
+
     def check(self, E, N, A, nb):
         want = [(E, N, 2), (E, A, 2), (E, nb, A, 2), (E, nb + 1, A, 2), (E, nb + 1, N, 2)]
         got = [tuple(t.shape) for t in (self.x0, self.xa0, self.burn_actions, self.agent_noise, self.particle_noise)]
@@ -67,8 +70,14 @@ class BatchedSwarmEnv(object):
     N_BURN_IN = 10
 
     def __init__(self, num_envs, n_locusts=None, n_agents=None, grid_size=84, max_episode_steps=128,
-                 seed=0, env_id_offset=0, device=None, math_mode="fast", auto_reset=True, rasterize=True):
+                 seed=0, env_id_offset=0, device=None, math_mode="fast", auto_reset=True, rasterize=True,
+                 binding="torch"):
+        """binding: "torch" = the hot calls go through torch.ops.swarm_b200.* (the C ABI as a PyTorch
+        extension, csrc/torch_binding.cpp), "ctypes" = straight into the C ABI.  Same kernels either way."""
         self.lib = nat.load()
+        if binding not in ("torch", "ctypes"):
+            raise ValueError("binding must be 'torch' or 'ctypes'")
+        self.ops = nat.load_torch_ops() if binding == "torch" else None
         if not torch.cuda.is_available():
             raise nat.SwarmNativeError("BatchedSwarmEnv needs a CUDA device (sm_100a); there is no CPU path")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -106,6 +115,15 @@ class BatchedSwarmEnv(object):
                                                            ctypes.byref(self._io))
         self._done_view = self.done_u8.view(torch.bool)
         self._was_reset = False
+        self.refresh_params()
+
+    def refresh_params(self):
+        self._state_t = (self.x, self.xa, self.noise_x, self.noise_a, self.elapsed, self.episode)
+
+    @property
+    def _blob(self):
+        """self.params (which callers may mutate, like the reference's class constants) packed for the torch ops."""
+        return nat.params_blob(self.params)
 
     # ------------------------------------------------------------------ gym surface
     def reset(self, mask=None, draws=None):
@@ -116,6 +134,11 @@ class BatchedSwarmEnv(object):
             m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         if draws is not None:
             draws.check(self.E, self.N, self.A, self.N_BURN_IN)
+        if self.ops is not None:
+            with torch.cuda.device(self.device):
+                self.ops.reset(self._blob, *self._state_t, m, draws.tensors() if draws is not None else [])
+            self._was_reset = True
+            return self.x, self.xa
         nat.check(self.lib.swarm_reset(ctypes.byref(self.params), ctypes.byref(self.state_c), _ptr(m),
                                        ctypes.byref(draws.c) if draws is not None else None,
                                        _stream(self.device)), "swarm_reset")
@@ -137,6 +160,13 @@ class BatchedSwarmEnv(object):
         rasterize = self.rasterize if rasterize is None else rasterize
         auto_reset = self.auto_reset if auto_reset is None else auto_reset
         flags = (nat.SWARM_STEP_AUTO_RESET if auto_reset else 0) | (nat.SWARM_STEP_CLIP_ACTIONS if clip else 0)
+        if self.ops is not None:
+            if actions.dtype not in (torch.float32, torch.float64):
+                raise ValueError("actions must be float32 or float64")
+            self.ops.step(self._blob, *self._state_t, actions, noise_a, noise_x, self.reward, self.done_u8,
+                          self.grid if rasterize else None, self.positions if rasterize else None, v_out, flags,
+                          reset_draws.tensors() if reset_draws is not None else [])
+            return (self.x, self.xa), self.reward, self._done_view, {}
         io = self._io                      # one persistent SwarmStepIO; only the per-call fields change
         if actions.dtype == torch.float32:
             io.actions_f32, io.actions_f64 = actions.data_ptr(), None
@@ -178,6 +208,9 @@ class BatchedSwarmEnv(object):
     # ------------------------------------------------------------------ observation
     def observe(self, box=None):
         """SwarmStateProcessor.process_state of the current state -> (grid, positions)."""
+        if self.ops is not None:
+            self.ops.rasterize(self._blob, self.x, self.xa, self.grid, self.positions, box)
+            return self.grid, self.positions
         nat.check(self.lib.swarm_rasterize(ctypes.byref(self.params), _ptr(self.x), _ptr(self.xa), _ptr(self.grid),
                                            _ptr(self.positions), _ptr(box), _stream(self.device)), "swarm_rasterize")
         return self.grid, self.positions
@@ -186,6 +219,9 @@ class BatchedSwarmEnv(object):
         """SwarmRunner.get_local_states for the batch: (E,A,G,G,3) f32 from self.grid/positions."""
         if out is None:
             out = torch.empty(self.E, self.A, self.G, self.G, 3, dtype=torch.float32, device=self.device)
+        if self.ops is not None:
+            self.ops.expand_obs(self._blob, self.grid, self.positions, out)
+            return out
         nat.check(self.lib.swarm_expand_obs(ctypes.byref(self.params), _ptr(self.grid), _ptr(self.positions),
                                             _ptr(out), _stream(self.device)), "swarm_expand_obs")
         return out
@@ -198,6 +234,9 @@ class BatchedSwarmEnv(object):
             v = torch.empty(self.E, self.N, 2, dtype=torch.float32, device=self.device)
         if reward is None:
             reward = torch.empty(self.E, dtype=torch.float32, device=self.device)
+        if self.ops is not None:
+            self.ops.forces(self._blob, x, xa, v, reward)
+            return v, reward
         nat.check(self.lib.swarm_forces(ctypes.byref(self.params), _ptr(x), _ptr(xa), _ptr(v), _ptr(reward),
                                         _stream(self.device)), "swarm_forces")
         return v, reward
@@ -262,6 +301,7 @@ class SwarmEnv(object):
                                            "F": "F", "L": "L", "dt": "dt"}[k], float(getattr(self, k)))
             self._env.params.n_burn_in = self.N_BURN_IN
             self._env.N_BURN_IN = self.N_BURN_IN
+            self._env.refresh_params()
         return self._env
 
     def _sync_out(self):

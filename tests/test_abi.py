@@ -100,3 +100,24 @@ def test_no_cpu_fallback_without_cuda(pkg):
     m = pkg.submodule("envs.multiagent")
     with pytest.raises(pkg.SwarmNativeError):
         m.BatchedSwarmEnv(4)
+
+
+def test_torch_extension_loads_and_registers_ops(pkg):
+    """The C ABI as a PyTorch extension (csrc/torch_binding.cpp): builds on CPU, registers
+    torch.ops.swarm_b200.*, validates arguments before touching the GPU."""
+    import torch
+    ops = pkg.load_torch_ops()
+    assert int(ops.abi_version()) == 1
+    for name in ("step", "reset", "rasterize", "expand_obs", "clip_actions", "forces"):
+        assert hasattr(ops, name)
+    with pytest.raises(RuntimeError):
+        ops.clip_actions(torch.zeros(4, 2), 1.0)                       # CPU tensor: refused, no CPU path
+    nat = pkg._native
+    p = nat.SwarmParams(n_envs=2, n_locusts=8, n_agents=10, grid_size=84, n_burn_in=10, max_episode_steps=128,
+                        math_mode=0, reserved=0, noise=1e-4, gravity=-1.0, wind=1.0, F=0.5, L=10.0, dt=0.05,
+                        box_width=3.0, box_height=3.0, seed=0, env_id_offset=0)
+    blob = nat.params_blob(p)
+    assert blob.dtype == torch.uint8 and blob.numel() == 112
+    with pytest.raises(RuntimeError):
+        ops.forces(blob[:10].clone(), torch.zeros(2, 8, 2, dtype=torch.float64), torch.zeros(2, 10, 2, dtype=torch.float64),
+                   None, None)                                         # wrong params size

@@ -72,3 +72,29 @@ def test_lr_annealing_matches_reference_formula(pkg, cuda):
     assert abs(L.get_lr() - 0.5e-4) < 1e-12
     L.global_step = 90000000
     assert L.get_lr() == 0.0
+
+
+def test_policy_monitor_eval_episode_and_json(pkg, cuda, tmp_path):
+    """policy_monitor.py:152-208: a seeded 'Swarm-eval-v0' episode runs to the 128-step TimeLimit, the best
+    score's actions land in swarm-eval.json in the format make_swarm_gif.py reads, and replaying them through
+    a fresh eval env reproduces the score (seed 192 makes the episode deterministic given the actions)."""
+    import json
+    import queue
+    L = make_learner(pkg, cuda, n_locusts=80)
+    pm = pkg.submodule("agents.paac.policy_monitor")
+    sp = pkg.submodule("agents.state_processors")
+    mon = pm.SwarmPolicyMonitor(global_policy_net=L.network, state_processor=sp.SwarmStateProcessor(grid_size=84),
+                                out_dir=str(tmp_path))
+    np.random.seed(5)
+    total, length, rewards = mon.eval_once()
+    assert length == 128 and len(rewards) == 128 and total < 0
+    d = json.load(open(tmp_path / "swarm-eval.json"))
+    assert abs(d["score"] - total) < 1e-9 and np.asarray(d["actions"]).shape == (128, 10, 2)
+    assert (np.linalg.norm(np.asarray(d["actions"]), axis=-1) <= 1 + 1e-6).all()
+    q = queue.Queue()
+    for a in d["actions"]:
+        q.put(a)
+    mon2 = pm.SwarmPolicyMonitor(global_policy_net=L.network, state_processor=sp.SwarmStateProcessor(grid_size=84),
+                                 out_dir=str(tmp_path))
+    total2, length2, _ = mon2.eval_once(actions=q)
+    assert length2 == 128 and abs(total2 - total) <= 1e-4 * abs(total)
