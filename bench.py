@@ -139,7 +139,7 @@ def paac_frames_per_sec(E_per_gpu, updates, warmup_updates, world, rank, local):
     args = tp.get_arg_parser().parse_args(["--height=84", "--clip_norm=1", "-ec", str(E_per_gpu * world)])
     net_creator, env_creator = tp.get_network_and_environment_creator(args)
     learner = pkg.submodule("agents.paac.paac").GridPAACLearner(net_creator, env_creator, args)
-    learner.runners.start(states_out=learner.states[0])
+    learner.start()
     for _ in range(warmup_updates):
         learner.update()
     torch.cuda.synchronize()
@@ -154,7 +154,9 @@ def paac_frames_per_sec(E_per_gpu, updates, warmup_updates, world, rank, local):
     frames = updates * learner.max_local_steps * learner.total_emulators
     return dict(frames_per_sec=frames / (ms * 1e-3), ms_per_update=ms / updates, updates=updates,
                 emulators=learner.total_emulators, local_steps=learner.max_local_steps,
-                policy_batch=learner.real_batch_size, net_dtype="fp32 (cuDNN TF32 convolutions, FP32 dense)",
+                policy_batch=learner.real_batch_size,
+                observation="compact (grid + positions; conv1 factorised over the shared channels)" if learner.compact_obs
+                else "expanded (E,A,84,84,3)", net_dtype="fp32 (cuDNN TF32 convolutions, FP32 dense)",
                 launch="one CUDA graph per update (rollout + returns + backward + all-reduce + Adam)")
 
 

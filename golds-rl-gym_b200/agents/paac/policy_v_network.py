@@ -63,6 +63,39 @@ class ConvSingleAgentPolicyNetwork(nn.Module):
         """states (B,H,W,C) float32 -> mu (B,num_actions), sigma (B,num_actions), vs (B,)."""
         x = states.permute(0, 3, 1, 2)                  # NHWC storage seen as channels_last NCHW: no copy
         x = F.relu(self.conv1(x))
+        return self._trunk_and_heads(x)
+
+    def forward_compact(self, grid, positions):
+        """The same function of the COMPACT observation: grid (E,H,W,C-1) float32 (the channels every agent of an
+        env shares) + positions (E,A,2) uint8 (each agent's one-hot cell in the last channel,
+        emulator_runner.py:98-111).  conv1 is linear, so conv1(expanded obs of agent a) =
+        conv1_{channels<C-1}(grid) [once per env] + the <= 4 kernel taps of the last channel that see the hot cell.
+        Saves 10x of conv1 and never materialises the (E,A,H,W,C) observation.  -> mu, sigma (E*A,.), vs (E*A,)."""
+        E, A = positions.shape[0], positions.shape[1]
+        C = self.channels
+        w = self.conv1.weight                                           # (32, C, 8, 8)
+        k, s = self.conv1.kernel_size[0], self.conv1.stride[0]
+        base = F.conv2d(grid.permute(0, 3, 1, 2), w[:, :C - 1], self.conv1.bias, stride=s)     # (E,32,oh,ow)
+        OH, OW, F1 = base.shape[2], base.shape[3], base.shape[1]
+        # per-agent maps in NHWC memory (what cuDNN's tensor-core kernels want): ONE materialising copy
+        x = base.permute(0, 2, 3, 1).reshape(E, 1, OH * OW, F1).expand(E, A, OH * OW, F1).reshape(E * A, OH * OW, F1)
+        pos = positions.reshape(E * A, 2).long()
+        h, wd = pos[:, 0], pos[:, 1]
+        w_hot = w[:, C - 1].reshape(F1, k * k)                          # (32, 64) taps of the one-hot channel
+        for dh in range((k + s - 1) // s):
+            oh = torch.div(h, s, rounding_mode="floor") - dh
+            kh = h - s * oh
+            for dw in range((k + s - 1) // s):
+                ow = torch.div(wd, s, rounding_mode="floor") - dw
+                kw = wd - s * ow
+                ok = (oh >= 0) & (oh < OH) & (ow >= 0) & (ow < OW) & (kh < k) & (kw < k)
+                tap = w_hot[:, (kh.clamp(max=k - 1) * k + kw.clamp(max=k - 1))].t() * ok[:, None].to(w_hot.dtype)   # (B,32)
+                idx = (oh.clamp(0, OH - 1) * OW + ow.clamp(0, OW - 1))[:, None, None].expand(-1, 1, F1)
+                x.scatter_add_(1, idx, tap[:, None, :])
+        x = F.relu_(x).view(E * A, OH, OW, F1).permute(0, 3, 1, 2)       # channels_last (B,32,oh,ow), no copy
+        return self._trunk_and_heads(x)
+
+    def _trunk_and_heads(self, x):
         x = F.relu(self.conv2(x))
         x = F.relu(self.conv3(x))
         x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)      # tf.layers.flatten of an NHWC tensor
@@ -80,9 +113,15 @@ class ConvSingleAgentPolicyNetwork(nn.Module):
         mu, sigma, vs = self.forward(states)
         return {"vs": vs, "mu": mu, "sigma": sigma}
 
-    def losses(self, states, actions, advantages, critic_target):
-        """-> dict(loss, policy_loss, critic_loss (B,), critic_loss_mean, mu, sigma, vs, entropy)."""
-        mu, sigma, vs = self.forward(states)
+    @torch.no_grad()
+    def predict_compact(self, grid, positions):
+        mu, sigma, vs = self.forward_compact(grid, positions)
+        return {"vs": vs, "mu": mu, "sigma": sigma}
+
+    def losses(self, states, actions, advantages, critic_target, positions=None):
+        """-> dict(loss, policy_loss, critic_loss (B,), critic_loss_mean, mu, sigma, vs, entropy).
+        With ``positions`` given, ``states`` is the compact (E,H,W,C-1) grid (see forward_compact)."""
+        mu, sigma, vs = self.forward(states) if positions is None else self.forward_compact(states, positions)
         var = sigma * sigma
         log_l = -((actions - mu) ** 2) / (2.0 * var) - torch.log(sigma) - 0.5 * math.log(2.0 * math.pi)
         entropy = 0.5 + 0.5 * math.log(2.0 * math.pi) + torch.log(sigma)

@@ -55,15 +55,18 @@ class GridRunners(object):
     def get_shared_variables(self):
         return self.variables
 
-    def update_environments(self, states_out=None):
+    def update_environments(self, states_out=None, grid_out=None, positions_out=None):
         """states_out: optional (E,A,G,G,3) tensor that receives the new expanded observation directly (the
         device-resident learner points it at its rollout ring, saving one 847 KB/env copy per step)."""
         if self.coord is not None and self.coord.should_stop():
             self.stop()
             return
         env = self.env
-        _, reward, done, _ = env.step(self.actions, rasterize=True, auto_reset=True)
-        if states_out is not None:
+        _, reward, done, _ = env.step(self.actions, rasterize=True, auto_reset=True, grid_out=grid_out,
+                                      positions_out=positions_out)
+        if grid_out is not None:
+            pass                                    # compact consumer: no expanded observation at all
+        elif states_out is not None:
             env.local_states(out=states_out)
         elif self.expand:
             env.local_states(out=self.states)

@@ -146,11 +146,13 @@ class BatchedSwarmEnv(object):
         return self.x, self.xa
 
     def step(self, actions, noise_a=None, noise_x=None, clip=False, reset_draws=None, v_out=None,
-             rasterize=None, auto_reset=None):
+             rasterize=None, auto_reset=None, grid_out=None, positions_out=None):
         """One env step for the whole batch; a single kernel launch.
 
         actions: (E,A,2) float32 or float64 CUDA tensor (float32 is the PAAC shared_actions dtype).
         With clip=True actions with |a|>=1 are normalised IN PLACE first (transform_actions_for_env).
+        grid_out / positions_out: optional (E,G,G,2) f32 / (E,A,2) u8 tensors that receive the observation
+        instead of self.grid / self.positions (e.g. a slot of a rollout ring).
         """
         if not self._was_reset:
             # the reference raises TypeError unpacking self.states=None (multiagent.py:31)
@@ -163,8 +165,10 @@ class BatchedSwarmEnv(object):
         if self.ops is not None:
             if actions.dtype not in (torch.float32, torch.float64):
                 raise ValueError("actions must be float32 or float64")
+            g_t = (grid_out if grid_out is not None else self.grid) if rasterize else None
+            p_t = (positions_out if positions_out is not None else self.positions) if rasterize else None
             self.ops.step(self._blob, *self._state_t, actions, noise_a, noise_x, self.reward, self.done_u8,
-                          self.grid if rasterize else None, self.positions if rasterize else None, v_out, flags,
+                          g_t, p_t, v_out, flags,
                           reset_draws.tensors() if reset_draws is not None else [])
             return (self.x, self.xa), self.reward, self._done_view, {}
         io = self._io                      # one persistent SwarmStepIO; only the per-call fields change
@@ -178,7 +182,8 @@ class BatchedSwarmEnv(object):
         io.noise_a = noise_a.data_ptr() if noise_a is not None else None
         io.noise_x = noise_x.data_ptr() if noise_x is not None else None
         if rasterize:
-            io.grid, io.positions = self._grid_ptr, self._pos_ptr
+            io.grid = grid_out.data_ptr() if grid_out is not None else self._grid_ptr
+            io.positions = positions_out.data_ptr() if positions_out is not None else self._pos_ptr
         else:
             io.grid, io.positions = None, None
         io.v_out = v_out.data_ptr() if v_out is not None else None

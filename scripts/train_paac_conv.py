@@ -87,6 +87,8 @@ def get_arg_parser():
     parser.add_argument('--no_cuda_graph', action='store_true')
     parser.add_argument('--reward_indexing', default='reference', choices=['reference', 'per_agent'])
     parser.add_argument('--mask_terminals', action='store_true')
+    parser.add_argument('--obs', default='auto', choices=['auto', 'compact', 'expanded'],
+                        help="observation the net consumes: compact = (grid, positions) with conv1 factorised")
     return parser
 
 
@@ -104,7 +106,8 @@ def main(args):
     network_creator, env_creator = get_network_and_environment_creator(args)
     paac = pkg.submodule("agents.paac.paac")
     learner = paac.GridPAACLearner(network_creator, env_creator, args, reward_indexing=args.reward_indexing,
-                                   mask_terminals=args.mask_terminals, use_cuda_graph=not args.no_cuda_graph)
+                                   mask_terminals=args.mask_terminals, use_cuda_graph=not args.no_cuda_graph,
+                                   compact_obs={"auto": "auto", "compact": True, "expanded": False}[args.obs])
 
     def on_signal(signum, frame):            # train_paac_conv.py:47-58
         learner.cleanup()

@@ -60,3 +60,30 @@ def test_gaussian_terms_match_torch_distributions(pkg):
     d = torch.distributions.Normal(out["mu"], out["sigma"])
     ref = -(d.log_prob(actions).sum(-1) * adv + 0.02 * d.entropy().sum(-1)).mean()
     assert torch.allclose(out["policy_loss"], ref, atol=1e-5)
+
+
+def test_compact_observation_forward_equals_expanded(pkg):
+    """conv1 factorisation: the net on (grid, positions) == the net on get_local_states(grid, positions), values and
+    gradients, including hot cells on the borders and in the last (clamped) row/column."""
+    torch.manual_seed(11)
+    net = make(pkg, 2, scale=1000.0, entropy_regularisation_strength=0.02).double()
+    E, A, G = 3, 10, 84
+    grid = torch.rand(E, G, G, 2, dtype=torch.float64) * (torch.rand(E, G, G, 2) > 0.98)
+    pos = torch.randint(0, G, (E, A, 2), dtype=torch.uint8)
+    pos[0, 0] = torch.tensor([0, 0]); pos[0, 1] = torch.tensor([83, 83]); pos[0, 2] = torch.tensor([3, 80])
+    pos[0, 3] = torch.tensor([4, 7]); pos[0, 4] = torch.tensor([79, 0])
+    expanded = torch.zeros(E, A, G, G, 3, dtype=torch.float64)
+    expanded[..., :2] = grid[:, None]
+    for e in range(E):
+        for a in range(A):
+            expanded[e, a, int(pos[e, a, 0]), int(pos[e, a, 1]), 2] = 1.0
+    act, adv, tgt = torch.randn(E * A, 2, dtype=torch.float64), torch.randn(E * A, dtype=torch.float64), -torch.rand(E * A, dtype=torch.float64)
+    o1 = net.losses(expanded.view(E * A, G, G, 3), act, adv, tgt)
+    g1 = torch.autograd.grad(o1["loss"], list(net.parameters()))
+    o2 = net.losses(grid, act, adv, tgt, positions=pos)
+    g2 = torch.autograd.grad(o2["loss"], list(net.parameters()))
+    for k in ("mu", "sigma", "vs"):
+        assert torch.allclose(o1[k], o2[k], rtol=1e-9, atol=1e-9), k
+    assert torch.allclose(o1["loss"], o2["loss"], rtol=1e-9)
+    for a_, b_ in zip(g1, g2):
+        assert torch.allclose(a_, b_, rtol=1e-7, atol=1e-10)
