@@ -559,3 +559,60 @@ def test_torch_extension_binding_equals_ctypes_binding(M):
     assert torch.equal(va, vb)
     with pytest.raises(ValueError):
         a.step(torch.zeros(E, 10, 2, device="cuda", dtype=torch.float16))
+
+
+@pytest.mark.parametrize("G", [2, 20, 83, 84, 85, 255])
+@pytest.mark.parametrize("A", [1, 10, 32])
+def test_rasterizer_grid_sizes_and_agent_counts(M, G, A):
+    """Fused and standalone rasteriser for other grid sizes (reference default grid_size=20; odd sizes take the
+    plain-store zero fill instead of the TMA one; 255 is the uint8 limit) and agent counts, bit-exact vs the
+    oracle, over two consecutive steps (the counter table must come back clean)."""
+    E, N = 5, 48
+    rs = np.random.RandomState(G * 100 + A)
+    if G == 255 and A == 32:        # 32 agents need 32-bit counters: 255^2 of them do not fit in shared memory
+        with pytest.raises(Exception):
+            M.BatchedSwarmEnv(E, n_locusts=N, n_agents=A, grid_size=G)
+        return
+    env = M.BatchedSwarmEnv(E, n_locusts=N, n_agents=A, grid_size=G, max_episode_steps=0, auto_reset=False)
+    x = rs.rand(E, N, 2) * [2.5, 1.2]
+    x[:, ::3, 1] = 0.0                                   # grounded locusts share y-bin 0
+    xa = rs.rand(E, A, 2) * [4.0, 7.0] - [0.5, 0.5]       # some agents outside the box
+    zeros_a, zeros_x = np.zeros((E, A, 2)), np.zeros((E, N, 2))
+    load_state(env, x, xa, zeros_a, zeros_x)
+    for t in range(2):
+        a = clipped(rs, (E, A, 2))
+        (gx, gxa), _, _, _ = env.step(to_dev(a))
+        gx, gxa = gx.cpu().numpy(), gxa.cpu().numpy()
+        fused_g, fused_p = env.grid.cpu().numpy().copy(), env.positions.cpu().numpy().copy()
+        g2, p2 = env.observe()
+        assert np.array_equal(fused_g, g2.cpu().numpy()) and np.array_equal(fused_p, p2.cpu().numpy())
+        for e in range(E):
+            g, p_ = so.rasterize(gx[e], gxa[e], G)
+            assert np.array_equal(fused_g[e], g.astype(np.float32)), (G, A, t, e)
+            assert np.array_equal(fused_p[e], p_), (G, A, t, e)
+
+
+def test_step_under_cuda_graph_replay_equals_eager(M):
+    """The rollout contract 'no host round trip': 8 captured steps replayed 20 times == 160 eager steps, bitwise
+    (crosses the 128-step auto-reset inside the graph)."""
+    E, N = 64, 64
+    acts = [torch.randn(E, 10, 2, device="cuda").clamp(-0.7, 0.7).contiguous() for _ in range(8)]
+    a = M.BatchedSwarmEnv(E, n_locusts=N, seed=21)
+    b = M.BatchedSwarmEnv(E, n_locusts=N, seed=21)
+    a.reset(); b.reset()
+    a.step(acts[0]); b.step(acts[0])                     # warm-up outside the capture (one-time attribute calls)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for i in range(8):
+            a.step(acts[i])
+    for _ in range(20):
+        g.replay()
+    for _ in range(20):
+        for i in range(8):
+            b.step(acts[i])
+    torch.cuda.synchronize()
+    for k in ("x", "xa", "elapsed", "episode", "grid", "positions", "reward", "done_u8"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert int(a.episode[0]) == 2
