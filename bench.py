@@ -377,8 +377,9 @@ def main():
                               "frac_hbm_peak": E * (G * G * 2 * 4 + A * 2 + (N + A) * 16) / (ms_r * 1e-3) / 1e9 / pk["hbm_gbs"]},
             "e2e": {"value": e2e_val, "unit": "locust-updates/s", "h2d_bytes_per_step": E * A * 2 * 4,
                     "d2h_bytes_per_step": E * 5, "ms_per_step": w_ms / K,
-                    "note": "swarm_step_host: pinned actions in, reward+done out, stream sync every step; "
-                            "observations stay in HBM for the device-resident policy"},
+                    "note": "swarm_step_host with pinned HOST buffers, one call + stream sync per step, wall clock: the kernel "
+                            "reads the step's actions from host memory over PCIe (cp.async prefetch, zero-copy) and posts "
+                            "reward+done into host memory; observations stay in HBM for the device-resident policy"},
             "gpu_launches": K,
             "clocks": clocks,
         }

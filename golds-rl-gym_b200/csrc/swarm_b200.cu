@@ -480,6 +480,17 @@ int check_launch(const char* what) {
         default: { constexpr int TT = 4; __VA_ARGS__; } break; \
     }
 
+// device-visible alias of a pinned (page-locked, UVA-mapped) host pointer, or nullptr
+template <typename T>
+T* mapped_host(T* host) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? static_cast<T*>(a.devicePointer) : nullptr;
+}
+
 const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
 bool draws_complete(const SwarmInjectedDraws* d) {
@@ -568,8 +579,27 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
     if (!p || !io || !host_actions || !host_reward || !host_done) return SWARM_ERR_NULL;
     if ((io->flags & SWARM_STEP_ACTIONS_F64) || !io->actions_f32) return SWARM_ERR_FLAGS;
     cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t err;
+    // Zero-copy path: with pinned host buffers the kernel itself pulls each env's 80 bytes of actions over
+    // PCIe (its cp.async prefetch runs one env ahead, so the latency hides under the previous env's force
+    // phase) and posts reward/done straight into host memory: no staging copies, one launch, one sync.
+    float* d_act = mapped_host(const_cast<float*>(host_actions));
+    float* d_rew = mapped_host(host_reward);
+    uint8_t* d_done = mapped_host(host_done);
+    if (d_act && d_rew && d_done) {
+        SwarmStepIO direct = *io;
+        direct.actions_f32 = d_act;
+        direct.reward = d_rew;
+        direct.done = d_done;
+        const int rc = swarm_step(p, st, &direct, nullptr, stream);
+        if (rc) return rc;
+        err = cudaStreamSynchronize(s);
+        if (err != cudaSuccess) return cuda_fail(err, "stream sync");
+        return SWARM_OK;
+    }
+    // Pageable host memory: staged copies through io->actions_f32 / io->reward / io->done.
     const size_t na = (size_t)p->n_envs * p->n_agents * 2 * sizeof(float);
-    cudaError_t err = cudaMemcpyAsync(io->actions_f32, host_actions, na, cudaMemcpyHostToDevice, s);
+    err = cudaMemcpyAsync(io->actions_f32, host_actions, na, cudaMemcpyHostToDevice, s);
     if (err != cudaSuccess) return cuda_fail(err, "H2D actions");
     const int rc = swarm_step(p, st, io, nullptr, stream);
     if (rc) return rc;

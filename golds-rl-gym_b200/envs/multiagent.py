@@ -114,6 +114,7 @@ class BatchedSwarmEnv(object):
         self._params_ref, self._state_ref, self._io_ref = (ctypes.byref(self.params), ctypes.byref(self.state_c),
                                                            ctypes.byref(self._io))
         self._done_view = self.done_u8.view(torch.bool)
+        self._io_host = None
         self._was_reset = False
         self.refresh_params()
 
@@ -197,17 +198,22 @@ class BatchedSwarmEnv(object):
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) form
     def step_host(self, host_actions, host_reward, host_done):
-        """swarm_step_host: actions come from / reward+done go to HOST (pinned) tensors; the
-        observation stays in HBM for the device-resident policy.  Synchronises the stream."""
-        io = nat.SwarmStepIO()
-        io.actions_f32 = _ptr(self.actions)
-        io.reward, io.done = _ptr(self.reward), _ptr(self.done_u8)
-        if self.rasterize:
-            io.grid, io.positions = _ptr(self.grid), _ptr(self.positions)
+        """swarm_step_host: actions come from / reward+done go to HOST tensors; the observation stays in HBM
+        for the device-resident policy.  Synchronises the stream.  Pinned tensors are read / written by the
+        kernel itself over PCIe (zero-copy); self.reward / self.done_u8 are then NOT updated."""
+        io = self._io_host
+        if io is None:
+            io = self._io_host = nat.SwarmStepIO()
+            io.actions_f32 = self.actions.data_ptr()
+            io.reward, io.done = self.reward.data_ptr(), self.done_u8.data_ptr()
+            self._io_host_ref = ctypes.byref(io)
+        io.grid, io.positions = (self._grid_ptr, self._pos_ptr) if self.rasterize else (None, None)
         io.flags = nat.SWARM_STEP_AUTO_RESET if self.auto_reset else 0
-        nat.check(self.lib.swarm_step_host(ctypes.byref(self.params), ctypes.byref(self.state_c), ctypes.byref(io),
-                                           _ptr(host_actions), _ptr(host_reward), _ptr(host_done),
-                                           _stream(self.device)), "swarm_step_host")
+        rc = self.lib.swarm_step_host(self._params_ref, self._state_ref, self._io_host_ref, host_actions.data_ptr(),
+                                      host_reward.data_ptr(), host_done.data_ptr(),
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            nat.check(rc, "swarm_step_host")
         return host_reward, host_done
 
     # ------------------------------------------------------------------ observation

@@ -123,9 +123,12 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
 int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                const SwarmInjectedDraws* reset_draws, swarm_stream_t stream);
 
-/* Same call with HOST buffers for the per-step inputs/results: copies host_actions (E,A,2 f32)
- * to io->actions_f32, runs swarm_step, copies io->reward / io->done back to host_reward /
- * host_done and synchronises the stream.  Pinned host memory makes the copies asynchronous. */
+/* Same call with HOST buffers for the per-step inputs/results; synchronises the stream before
+ * returning.  With PINNED host buffers (cudaHostAlloc / torch pin_memory: device-visible under
+ * UVA) the kernel reads host_actions and writes host_reward / host_done directly over PCIe --
+ * no staging copies (io->actions_f32 / io->reward / io->done are then left untouched).  With
+ * pageable memory it copies host_actions to io->actions_f32, runs swarm_step and copies
+ * io->reward / io->done back. */
 int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                     const float* host_actions, float* host_reward, uint8_t* host_done,
                     swarm_stream_t stream);

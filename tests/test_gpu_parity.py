@@ -476,14 +476,18 @@ def test_seeded_facade_matches_reference_golden(M):
 
 
 # --------------------------------------------------------------------------------------- host buffers
-def test_step_host_matches_device_step(M):
-    E, N = 32, 64
-    a = M.BatchedSwarmEnv(E, n_locusts=N, seed=5)
-    b = M.BatchedSwarmEnv(E, n_locusts=N, seed=5)
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_matches_device_step(M, pinned):
+    """swarm_step_host: pinned buffers take the zero-copy path (the kernel reads the actions from and writes
+    reward/done to host memory), pageable ones the staged-copy path; both equal the device-resident step."""
+    E, N = 300, 64
+    a = M.BatchedSwarmEnv(E, n_locusts=N, seed=5, max_episode_steps=2)
+    b = M.BatchedSwarmEnv(E, n_locusts=N, seed=5, max_episode_steps=2)
     a.reset(); b.reset()
-    h_act = torch.randn(E, 10, 2).clamp_(-0.5, 0.5).pin_memory()
-    h_rew = torch.zeros(E).pin_memory()
-    h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    h_act = pin(torch.randn(E, 10, 2).clamp_(-0.5, 0.5))
+    h_rew = pin(torch.zeros(E))
+    h_done = pin(torch.zeros(E, dtype=torch.uint8))
     for t in range(3):
         a.step_host(h_act, h_rew, h_done)
         _, r, d, _ = b.step(h_act.cuda())
