@@ -23,6 +23,7 @@ c_void_p, c_int, c_int32, c_int64, c_uint32, c_uint64, c_double, c_float = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
     ctypes.c_double, ctypes.c_float)
 
+ABI_VERSION = 2
 SWARM_STEP_AUTO_RESET = 1
 SWARM_STEP_CLIP_ACTIONS = 2
 SWARM_STEP_ACTIONS_F64 = 4
@@ -39,7 +40,7 @@ class SwarmParams(ctypes.Structure):
 
 class SwarmState(ctypes.Structure):
     _fields_ = [("x", c_void_p), ("xa", c_void_p), ("noise_x", c_void_p), ("noise_a", c_void_p),
-                ("elapsed", c_void_p), ("episode", c_void_p)]
+                ("elapsed", c_void_p), ("episode", c_void_p), ("work", c_void_p)]
 
 
 class SwarmInjectedDraws(ctypes.Structure):
@@ -137,7 +138,7 @@ def load():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.swarm_abi_version() != 1:
+    if lib.swarm_abi_version() != ABI_VERSION:
         raise SwarmNativeError("ABI version mismatch: %d" % lib.swarm_abi_version())
     _lib = lib
     return lib
@@ -203,7 +204,7 @@ def load_torch_ops():
             if not os.path.isfile(TORCH_LIB_PATH):
                 raise
     torch.ops.load_library(TORCH_LIB_PATH)
-    if int(torch.ops.swarm_b200.abi_version()) != 1:
+    if int(torch.ops.swarm_b200.abi_version()) != ABI_VERSION:
         raise SwarmNativeError("torch extension ABI version mismatch")
     _torch_ops = torch.ops.swarm_b200
     return _torch_ops

@@ -45,6 +45,8 @@ struct KP {
     float F, nInvL, U, Gv, eps_s;
     uint2 key;
     uint32_t env_off;
+    int n_sms;        // SMs of the device
+    int dynamic;      // k_step: draw the third and later envs of a CTA from the work queue (SwarmState::work)
 };
 
 // One STAGE buffer = what is prefetched for the step of one env (the locust noise row follows
@@ -71,6 +73,7 @@ struct Smem {
     float2* slot;     // MODE 1/3: nt x nslots x 32 reaction-force partial sums
     // ---- rasteriser (present when the kernel rasterises)
     double2* rx;      // N+A: post-step positions handed from the force to the raster group
+    int* mail;        // [0] env id handed to the raster group (-1 = no more), [1] next env grabbed from the work queue
     uint32_t* table;  // G*G packed cell counters, 16 bits per cell (two cells per word): locusts in the low
                       // bits, agents above them (kAgentShift); 32 bits per cell (locusts lo16, agents hi16)
                       // when the counts do not fit
@@ -87,7 +90,7 @@ __host__ __device__ inline size_t smem_src_bytes(int N, int A, int sym) {
 }
 __host__ __device__ inline size_t smem_fixed_bytes(int N, int A) {
     return smem_align(sizeof(double2) * N) + smem_align(sizeof(double2) * A) + smem_align(sizeof(double) * 32) +
-           smem_align(sizeof(double) * 2);
+           smem_align(sizeof(double) * 2) + 16;
 }
 // 16-bit cell counters hold (locusts | agents << kAgentShift) when N < 2^kAgentShift and A < 2^(16-kAgentShift)
 constexpr int kAgentShift = 11;
@@ -132,6 +135,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     s.act = reinterpret_cast<double2*>(base + o); o += smem_align(sizeof(double2) * A);
     s.red = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 32);
     s.box = reinterpret_cast<double*>(base + o);  o += smem_align(sizeof(double) * 2);
+    s.mail = reinterpret_cast<int*>(base + o);    o += 16;
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
     if (force) o += smem_force_bytes(N, A, sym);

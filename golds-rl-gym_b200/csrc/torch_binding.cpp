@@ -43,7 +43,8 @@ T* ptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<
 swarm_stream_t stream_of(const at::Tensor& t) { return (swarm_stream_t)c10::cuda::getCurrentCUDAStream(t.get_device()).stream(); }
 
 SwarmState make_state(const SwarmParams& p, const at::Tensor& x, const at::Tensor& xa, const at::Tensor& noise_x,
-                      const at::Tensor& noise_a, const at::Tensor& elapsed, const at::Tensor& episode) {
+                      const at::Tensor& noise_a, const at::Tensor& elapsed, const at::Tensor& episode,
+                      const c10::optional<at::Tensor>& work = c10::nullopt) {
     const int64_t E = p.n_envs, N = p.n_locusts, A = p.n_agents;
     need(x, at::kDouble, {E, N, 2}, "x");
     need(xa, at::kDouble, {E, A, 2}, "xa");
@@ -51,8 +52,10 @@ SwarmState make_state(const SwarmParams& p, const at::Tensor& x, const at::Tenso
     need(noise_a, at::kDouble, {E, A, 2}, "noise_a");
     need(elapsed, at::kInt, {E}, "elapsed");
     need(episode, at::kInt, {E}, "episode");
+    if (work.has_value()) need(*work, at::kInt, {2}, "work");
     return SwarmState{x.data_ptr<double>(), xa.data_ptr<double>(), noise_x.data_ptr<double>(), noise_a.data_ptr<double>(),
-                      elapsed.data_ptr<int32_t>(), reinterpret_cast<uint32_t*>(episode.data_ptr<int32_t>())};
+                      elapsed.data_ptr<int32_t>(), reinterpret_cast<uint32_t*>(episode.data_ptr<int32_t>()),
+                      work.has_value() ? reinterpret_cast<uint32_t*>(work->data_ptr<int32_t>()) : nullptr};
 }
 
 SwarmStepIO make_io(const SwarmParams& p, const at::Tensor& actions, const c10::optional<at::Tensor>& noise_a_step,
@@ -102,12 +105,12 @@ SwarmInjectedDraws make_draws(const SwarmParams& p, const at::TensorList& d) {
 
 // SwarmEnv._step + TimeLimit (+ auto-reset, + process_state): one kernel launch on the current stream
 void op_step(const at::Tensor& params, at::Tensor x, at::Tensor xa, at::Tensor noise_x, at::Tensor noise_a, at::Tensor elapsed,
-             at::Tensor episode, at::Tensor actions, c10::optional<at::Tensor> noise_a_step,
+             at::Tensor episode, c10::optional<at::Tensor> work, at::Tensor actions, c10::optional<at::Tensor> noise_a_step,
              c10::optional<at::Tensor> noise_x_step, at::Tensor reward, at::Tensor done, c10::optional<at::Tensor> grid,
              c10::optional<at::Tensor> positions, c10::optional<at::Tensor> v_out, int64_t flags, at::TensorList reset_draws) {
     const SwarmParams p = unpack(params);
     c10::cuda::CUDAGuard guard(x.device());
-    const SwarmState st = make_state(p, x, xa, noise_x, noise_a, elapsed, episode);
+    const SwarmState st = make_state(p, x, xa, noise_x, noise_a, elapsed, episode, work);
     const SwarmStepIO io = make_io(p, actions, noise_a_step, noise_x_step, reward, done, grid, positions, v_out, flags);
     SwarmInjectedDraws dr;
     if (reset_draws.size()) dr = make_draws(p, reset_draws);
@@ -182,7 +185,7 @@ int64_t op_abi_version() { return swarm_abi_version(); }
 
 TORCH_LIBRARY(swarm_b200, m) {
     m.def("step(Tensor params, Tensor(a!) x, Tensor(b!) xa, Tensor(c!) noise_x, Tensor(d!) noise_a, Tensor(e!) elapsed, "
-          "Tensor(f!) episode, Tensor(g!) actions, Tensor? noise_a_step, Tensor? noise_x_step, Tensor(h!) reward, "
+          "Tensor(f!) episode, Tensor(m!)? work, Tensor(g!) actions, Tensor? noise_a_step, Tensor? noise_x_step, Tensor(h!) reward, "
           "Tensor(i!) done, Tensor(j!)? grid, Tensor(k!)? positions, Tensor(l!)? v_out, int flags, Tensor[] reset_draws) -> ()",
           &op_step);
     m.def("reset(Tensor params, Tensor(a!) x, Tensor(b!) xa, Tensor(c!) noise_x, Tensor(d!) noise_a, Tensor(e!) elapsed, "

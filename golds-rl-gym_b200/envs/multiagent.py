@@ -101,13 +101,14 @@ class BatchedSwarmEnv(object):
         self.noise_a = torch.zeros(E, A, 2, dtype=f64, device=d)
         self.elapsed = torch.zeros(E, dtype=torch.int32, device=d)
         self.episode = torch.zeros(E, dtype=torch.int32, device=d)      # uint32 on the device side
+        self.work = torch.zeros(2, dtype=torch.int32, device=d)         # swarm_step's work queue (zero between calls)
         self.actions = torch.zeros(E, A, 2, dtype=torch.float32, device=d)
         self.reward = torch.zeros(E, dtype=torch.float32, device=d)
         self.done_u8 = torch.zeros(E, dtype=torch.uint8, device=d)
         self.grid = torch.zeros(E, G, G, 2, dtype=torch.float32, device=d)
         self.positions = torch.zeros(E, A, 2, dtype=torch.uint8, device=d)
         self.state_c = nat.SwarmState(_ptr(self.x), _ptr(self.xa), _ptr(self.noise_x), _ptr(self.noise_a),
-                                      _ptr(self.elapsed), _ptr(self.episode))
+                                      _ptr(self.elapsed), _ptr(self.episode), _ptr(self.work))
         self._io = nat.SwarmStepIO()
         self._io.reward, self._io.done = self.reward.data_ptr(), self.done_u8.data_ptr()
         self._grid_ptr, self._pos_ptr = self.grid.data_ptr(), self.positions.data_ptr()
@@ -119,7 +120,7 @@ class BatchedSwarmEnv(object):
         self.refresh_params()
 
     def refresh_params(self):
-        self._state_t = (self.x, self.xa, self.noise_x, self.noise_a, self.elapsed, self.episode)
+        self._state_t = (self.x, self.xa, self.noise_x, self.noise_a, self.elapsed, self.episode, self.work)
 
     @property
     def _blob(self):
@@ -137,7 +138,7 @@ class BatchedSwarmEnv(object):
             draws.check(self.E, self.N, self.A, self.N_BURN_IN)
         if self.ops is not None:
             with torch.cuda.device(self.device):
-                self.ops.reset(self._blob, *self._state_t, m, draws.tensors() if draws is not None else [])
+                self.ops.reset(self._blob, *self._state_t[:6], m, draws.tensors() if draws is not None else [])
             self._was_reset = True
             return self.x, self.xa
         nat.check(self.lib.swarm_reset(ctypes.byref(self.params), ctypes.byref(self.state_c), _ptr(m),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 1
+#define SWARM_ABI_VERSION 2
 
 /* opaque: a cudaStream_t passed as a pointer-sized handle (0 = legacy default stream) */
 typedef void* swarm_stream_t;
@@ -73,6 +73,10 @@ typedef struct SwarmState {
     double* noise_a;            /* (E,A,2) unscaled N(0,1) */
     int32_t* elapsed;           /* (E) steps since reset   */
     uint32_t* episode;          /* (E) resets so far (Philox counter word) */
+    uint32_t* work;             /* nullable (2): scratch words, ZERO when handed over and zero again after every
+                                 * call.  With them swarm_step hands envs to its persistent CTAs through a work
+                                 * queue (dynamic balance, de-synchronised CTAs); without, envs are assigned
+                                 * statically.  Not shared between concurrently running calls. */
 } SwarmState;
 
 /* The reference's random draws of one reset (multiagent.py:51-56), injected for parity tests.

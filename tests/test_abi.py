@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_bound(pkg):
         assert hasattr(lib, n), "libswarm_b200.so does not export %s" % n
         assert n in nat.SYMBOLS, "ctypes binding misses %s" % n
     assert sorted(nat.SYMBOLS) == names
-    assert lib.swarm_abi_version() == 1
+    assert lib.swarm_abi_version() == 2
     assert lib.swarm_strerror(0) == b"ok" and b"NULL" in lib.swarm_strerror(-1)
 
 
@@ -107,7 +107,7 @@ def test_torch_extension_loads_and_registers_ops(pkg):
     torch.ops.swarm_b200.*, validates arguments before touching the GPU."""
     import torch
     ops = pkg.load_torch_ops()
-    assert int(ops.abi_version()) == 1
+    assert int(ops.abi_version()) == 2
     for name in ("step", "reset", "rasterize", "expand_obs", "clip_actions", "forces"):
         assert hasattr(ops, name)
     with pytest.raises(RuntimeError):
