@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -174,6 +175,10 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                 if (g.tid == 0) sm.mail[0] = e;
                 bar_arrive<BAR_FULL>(n_all);
             }
+            if (kp.publish) {   // tell the concurrently running k_raster_follow that env e's new state is in memory
+                g.sync();
+                if (g.tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(work + 2 + e), "r"(1u) : "memory");
+            }
             e = e1;
             if (!dyn) e1 = e + gridDim.x;
         }
@@ -241,6 +246,49 @@ __global__ void __maxnreg__(64) k_reset(const KP kp, const SwarmState st, const 
     if (g.tid == 0) {
         st.elapsed[e] = 0;
         st.episode[e] = ep + 1;
+    }
+}
+
+// SwarmStateProcessor.process_state of the state k_step is producing RIGHT NOW: a persistent kernel on a second,
+// higher-priority stream that runs concurrently with a rasteriser-less k_step.  It streams out an env's zeros,
+// waits for k_step to publish the env (ready[e], release/acquire), reads the fresh positions from L2, rasterises
+// and clears the flag again.  k_step then runs in its fastest shape (one hardware-scheduled CTA per env) and the
+// rasteriser's latency chains cost it no shared memory, registers or barriers.
+__global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double* __restrict__ x,
+                                                       const double* __restrict__ xa, float* __restrict__ grid,
+                                                       uint8_t* __restrict__ positions, uint32_t* ready) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = kp.N, A = kp.A, cells = kp.G * kp.G;
+    const Smem sm = carve(smem_raw, N, A, kp.G, 0, false, 0);
+    const RGrp g = {(int)threadIdx.x, (int)blockDim.x};
+    const bool tma = tma_zero_fill_ok(grid, cells);
+    const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
+    raster_table_clear(sm, (int)(table_bytes / 4), g);
+    g.sync();
+    double2* pts = sm.rx;
+    for (int e = blockIdx.x; e < kp.E; e += gridDim.x) {
+        float* grid_e = grid + (size_t)e * cells * 2;
+        if (tma) {
+            if (g.tid == 0) tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
+        } else {
+            raster_zero_fill(grid_e, cells, g.tid, g.n);
+        }
+        if (g.tid == 0) {
+            uint32_t v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + e) : "memory");
+                if (v) break;
+                __nanosleep(200);
+            }
+        }
+        g.sync();
+        const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * N;     // fresh data: L2, not L1
+        const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * A;
+        for (int i = g.tid; i < N; i += g.n) pts[i] = __ldcg(gx + i);
+        for (int k = g.tid; k < A; k += g.n) pts[N + k] = __ldcg(ga + k);
+        g.sync();
+        env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, NoRelease());
+        if (g.tid == 0) ready[e] = 0u;          // consumed: the next step's k_step raises it again
     }
 }
 
@@ -440,14 +488,22 @@ KP make_kp(const SwarmParams* p) {
     k.env_off = (uint32_t)p->env_id_offset;
     k.n_sms = 1;
     k.dynamic = 0;
+    k.publish = 0;
     return k;
 }
 
 // Per (device, kernel) launch cache: the opt-in shared-memory ceiling already granted and the
 // occupancy (CTAs/SM) of the configurations seen, so that the steady-state cost of an entry
 // point is one cudaGetDevice + one launch.
+// side stream (higher priority) + fork/join events of the two-kernel step, one set per device
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+
 struct KernelCache {
     std::mutex mu;
+    std::map<int, SideStream> side;
     std::map<std::pair<int, const void*>, size_t> smem_set;
     std::map<std::tuple<int, const void*, int, size_t>, int> occupancy;
     std::map<int, int> sms;
@@ -464,13 +520,21 @@ int current_device(int* dev) {
 
 template <typename K>
 int prep(K kernel, size_t smem) {
-    if (smem <= 48 * 1024) return SWARM_OK;
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;
     KernelCache& c = cache();
     std::lock_guard<std::mutex> lk(c.mu);
-    size_t& have = c.smem_set[std::make_pair(dev, (const void*)kernel)];
-    if (smem > have) {
+    auto key = std::make_pair(dev, (const void*)kernel);
+    const bool first = c.smem_set.find(key) == c.smem_set.end();
+    size_t& have = c.smem_set[key];
+    if (first) {
+        // every kernel asks for the same (maximal) shared-memory carve-out: an SM cannot change its L1/shared split
+        // while a CTA is resident, and the step and its follower must be able to share SMs
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               (int)cudaSharedmemCarveoutMaxShared);
+        if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(carveout)");
+    }
+    if (smem > 48 * 1024 && smem > have) {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute");
         have = smem;
@@ -496,7 +560,9 @@ int persistent_grid(K kernel, int threads, size_t smem, int n_envs, int* grid, i
     auto o = c.occupancy.find(key);
     if (o == c.occupancy.end()) {
         int per_sm = 0;
-        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        cudaFuncAttributes fa;
+        cudaError_t err = cudaFuncGetAttributes(&fa, kernel);        // also forces the (lazily loaded) kernel in
+        if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
         if (err != cudaSuccess) return cuda_fail(err, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
         if (per_sm < 1) per_sm = 1;
         o = c.occupancy.emplace(key, per_sm).first;
@@ -504,6 +570,27 @@ int persistent_grid(K kernel, int threads, size_t smem, int n_envs, int* grid, i
     const long long slots = (long long)s->second * o->second;
     *grid = (int)(n_envs < slots ? n_envs : slots);
     if (n_sms) *n_sms = s->second;
+    return SWARM_OK;
+}
+
+int side_stream(SideStream* out) {
+    int dev = 0;
+    if (int rc = current_device(&dev)) return rc;
+    KernelCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    SideStream& ss = c.side[dev];
+    if (!ss.stream) {
+        int lo = 0, hi = 0;
+        cudaError_t err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, hi);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming);
+        if (err != cudaSuccess) {
+            ss = SideStream();
+            return cuda_fail(err, "side stream");
+        }
+    }
+    *out = ss;
     return SWARM_OK;
 }
 
@@ -529,6 +616,17 @@ T* mapped_host(T* host) {
         return nullptr;
     }
     return a.type == cudaMemoryTypeHost ? static_cast<T*>(a.devicePointer) : nullptr;
+}
+
+typedef void (*StepKernel)(const KP, const SwarmState, const SwarmStepIO, const SwarmInjectedDraws, const int, const int);
+
+StepKernel step_kernel(int mode, bool precise) {
+    switch (mode) {
+        case 1: return precise ? k_step<1, true> : k_step<1, false>;
+        case 2: return precise ? k_step<2, true> : k_step<2, false>;
+        case 3: return precise ? k_step<3, true> : k_step<3, false>;
+        default: return precise ? k_step<4, true> : k_step<4, false>;
+    }
 }
 
 const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -593,37 +691,62 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
     if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
     KP kp = make_kp(p);
-    const bool raster = io->grid != nullptr;
+    const bool want_grid = io->grid != nullptr;
+    // With the scratch words (SwarmState::work, 2 + E of them) the observation is produced by a second kernel that
+    // follows the step on a higher-priority stream (k_raster_follow); without, by the raster warps of k_step itself.
+    // The follower spins until the step publishes an env, so the step must always be able to get onto an SM next to it.
+    const int follow_threads = (kp.N + kp.A) <= 128 ? 32 : 128;
+    const size_t follow_smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, true, 0);
+    int follow_per_sm = (kp.N + kp.A) <= 128 ? 6 : 2;            // raster CTAs per SM that keep pace with the step
+    while (follow_per_sm > 0 && follow_per_sm * (follow_smem + 1024) + step_smem(p, false) + 1024 > kMaxSmem) --follow_per_sm;
+    // Measured (B200, 4096 envs): the follower wins for large swarms (N = 256: 0.181 vs 0.199 ms, N = 192: 0.123 vs
+    // 0.135), the in-kernel raster warps for small ones, where the rasteriser -- not the forces -- is the critical path
+    // (N = 128: 0.080 vs 0.108 ms, N = 64: 0.052 vs 0.069); N = 160 is the break-even.
+    const bool follow = want_grid && st->work != nullptr && kp.N >= 160 && follow_per_sm > 0 &&
+                        follow_per_sm * follow_threads + block_threads(kp.N) <= 2048;
+    const bool raster = want_grid && !follow;
     const size_t smem = step_smem(p, raster);
     const int nf = block_threads(kp.N);
     const int nt = nf + (raster ? raster_threads(kp.N, kp.A) : 0);
     const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;
     const int has = reset_draws ? 1 : 0;
-    const int mode = force_mode(kp.N);
-    int grid = 0;
     cudaStream_t s = (cudaStream_t)stream;
-    // The work queue pays off when every CTA has several large envs to work through (one contended atomic
-    // per env); small or few envs keep the static stride.
-    auto tune = [&](int& g, int sms) {
-        kp.n_sms = sms > 0 ? sms : 1;
-        // without a rasteriser to overlap there is nothing to gain from persistence, and hardware-scheduled
-        // one-env CTAs measure 8 % faster (C4: 0.154 vs 0.166 ms)
-        if (!raster) g = kp.E;
-        kp.dynamic = (st->work && kp.E >= 3 * g && (long long)kp.N * (kp.N + kp.A) >= 16384) ? 1 : 0;
-    };
-    int sms = 1;
-    DISPATCH_T(mode,
-        if (p->math_mode) {
-            if ((rc = prep(k_step<TT, true>, smem))) return rc;
-            if ((rc = persistent_grid(k_step<TT, true>, nt, smem, kp.E, &grid, &sms))) return rc;
-            tune(grid, sms);
-            k_step<TT, true><<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
-        } else {
-            if ((rc = prep(k_step<TT, false>, smem))) return rc;
-            if ((rc = persistent_grid(k_step<TT, false>, nt, smem, kp.E, &grid, &sms))) return rc;
-            tune(grid, sms);
-            k_step<TT, false><<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
-        })
+    const StepKernel kernel = step_kernel(force_mode(kp.N), p->math_mode != 0);
+    // Everything that may load code or touch the context happens BEFORE the follower is launched: with lazy module
+    // loading the first use of a kernel can synchronise the context, which would dead-lock against a follower
+    // that is already spinning on its ready flags.
+    if ((rc = prep(kernel, smem))) return rc;
+    int grid = 0, sms = 1;
+    if ((rc = persistent_grid(kernel, nt, smem, kp.E, &grid, &sms))) return rc;
+    kp.n_sms = sms > 0 ? sms : 1;
+    // without raster warps to overlap there is nothing to gain from persistence, and hardware-scheduled one-env
+    // CTAs measure 8 % faster (C4: 0.154 vs 0.166 ms)
+    if (!raster) grid = kp.E;
+    // the work queue pays off when every CTA has several large envs to work through (one contended atomic per env)
+    kp.dynamic = (raster && st->work && kp.E >= 3 * grid && (long long)kp.N * (kp.N + kp.A) >= 16384) ? 1 : 0;
+    SideStream ss;
+    if (follow) {
+        if ((rc = side_stream(&ss))) return rc;
+        const int rt = follow_threads;
+        const size_t rsmem = follow_smem;
+        if ((rc = prep(k_raster_follow, rsmem))) return rc;
+        int rgrid = 0;
+        if ((rc = persistent_grid(k_raster_follow, rt, rsmem, kp.E, &rgrid))) return rc;
+        if (rgrid > sms * follow_per_sm) rgrid = sms * follow_per_sm;
+        cudaError_t err = cudaEventRecord(ss.fork, s);
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(ss.stream, ss.fork, 0);
+        if (err != cudaSuccess) return cuda_fail(err, "fork");
+        k_raster_follow<<<rgrid, rt, rsmem, ss.stream>>>(kp, st->x, st->xa, io->grid, io->positions, st->work + 2);
+        if ((rc = check_launch("k_raster_follow"))) return rc;
+        kp.publish = 1;
+    }
+    kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
+    if (follow) {
+        if ((rc = check_launch("swarm_step"))) return rc;
+        cudaError_t err = cudaEventRecord(ss.join, ss.stream);
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(s, ss.join, 0);
+        if (err != cudaSuccess) return cuda_fail(err, "join");
+    }
     return check_launch("swarm_step");
 }
 

@@ -47,6 +47,7 @@ struct KP {
     uint32_t env_off;
     int n_sms;        // SMs of the device
     int dynamic;      // k_step: draw the third and later envs of a CTA from the work queue (SwarmState::work)
+    int publish;      // k_step: raise work[2 + e] once env e's new state is in memory (k_raster_follow waits for it)
 };
 
 // One STAGE buffer = what is prefetched for the step of one env (the locust noise row follows

@@ -52,7 +52,7 @@ SwarmState make_state(const SwarmParams& p, const at::Tensor& x, const at::Tenso
     need(noise_a, at::kDouble, {E, A, 2}, "noise_a");
     need(elapsed, at::kInt, {E}, "elapsed");
     need(episode, at::kInt, {E}, "episode");
-    if (work.has_value()) need(*work, at::kInt, {2}, "work");
+    if (work.has_value()) need(*work, at::kInt, {2 + E}, "work");
     return SwarmState{x.data_ptr<double>(), xa.data_ptr<double>(), noise_x.data_ptr<double>(), noise_a.data_ptr<double>(),
                       elapsed.data_ptr<int32_t>(), reinterpret_cast<uint32_t*>(episode.data_ptr<int32_t>()),
                       work.has_value() ? reinterpret_cast<uint32_t*>(work->data_ptr<int32_t>()) : nullptr};

@@ -101,7 +101,7 @@ class BatchedSwarmEnv(object):
         self.noise_a = torch.zeros(E, A, 2, dtype=f64, device=d)
         self.elapsed = torch.zeros(E, dtype=torch.int32, device=d)
         self.episode = torch.zeros(E, dtype=torch.int32, device=d)      # uint32 on the device side
-        self.work = torch.zeros(2, dtype=torch.int32, device=d)         # swarm_step's work queue (zero between calls)
+        self.work = torch.zeros(2 + E, dtype=torch.int32, device=d)     # swarm_step's scratch: queue + per-env ready flags
         self.actions = torch.zeros(E, A, 2, dtype=torch.float32, device=d)
         self.reward = torch.zeros(E, dtype=torch.float32, device=d)
         self.done_u8 = torch.zeros(E, dtype=torch.uint8, device=d)

@@ -73,10 +73,11 @@ typedef struct SwarmState {
     double* noise_a;            /* (E,A,2) unscaled N(0,1) */
     int32_t* elapsed;           /* (E) steps since reset   */
     uint32_t* episode;          /* (E) resets so far (Philox counter word) */
-    uint32_t* work;             /* nullable (2): scratch words, ZERO when handed over and zero again after every
-                                 * call.  With them swarm_step hands envs to its persistent CTAs through a work
-                                 * queue (dynamic balance, de-synchronised CTAs); without, envs are assigned
-                                 * statically.  Not shared between concurrently running calls. */
+    uint32_t* work;             /* nullable (2 + E): scratch words, ZERO when handed over and zero again after every
+                                 * call.  With them swarm_step produces the observation with a second kernel that
+                                 * follows the step on an internal higher-priority stream (per-env ready flags in
+                                 * work[2..]); without, with raster warps inside the step kernel (static env
+                                 * assignment).  Not shared between concurrently running calls. */
 } SwarmState;
 
 /* The reference's random draws of one reset (multiagent.py:51-56), injected for parity tests.
