@@ -380,7 +380,7 @@ def main():
                     "note": "swarm_step_host with pinned HOST buffers, one call + stream sync per step, wall clock: the kernel "
                             "reads the step's actions from host memory over PCIe (cp.async prefetch, zero-copy) and posts "
                             "reward+done into host memory; observations stay in HBM for the device-resident policy"},
-            "gpu_launches": K,
+            "gpu_launches": K * (2 if N >= 160 else 1),      # k_step (+ k_raster_follow for large swarms) per step
             "clocks": clocks,
         }
         if cpu:

@@ -712,9 +712,6 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     const int has = reset_draws ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const StepKernel kernel = step_kernel(force_mode(kp.N), p->math_mode != 0);
-    // Everything that may load code or touch the context happens BEFORE the follower is launched: with lazy module
-    // loading the first use of a kernel can synchronise the context, which would dead-lock against a follower
-    // that is already spinning on its ready flags.
     if ((rc = prep(kernel, smem))) return rc;
     int grid = 0, sms = 1;
     if ((rc = persistent_grid(kernel, nt, smem, kp.E, &grid, &sms))) return rc;
@@ -724,29 +721,32 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (!raster) grid = kp.E;
     // the work queue pays off when every CTA has several large envs to work through (one contended atomic per env)
     kp.dynamic = (raster && st->work && kp.E >= 3 * grid && (long long)kp.N * (kp.N + kp.A) >= 16384) ? 1 : 0;
+    if (!follow) {
+        kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
+        return check_launch("swarm_step");
+    }
+    // Step first, follower second: if anything serialises the two launches (a profiler, CUDA_LAUNCH_BLOCKING, a
+    // device that cannot co-schedule them) the step simply finishes before the follower starts and finds every
+    // flag raised -- slower, never dead-locked.  Run concurrently, the follower's CTAs (higher-priority stream)
+    // take the first SM slots the step's one-env CTAs free up and then trail it by one env.
     SideStream ss;
-    if (follow) {
-        if ((rc = side_stream(&ss))) return rc;
-        const int rt = follow_threads;
-        const size_t rsmem = follow_smem;
-        if ((rc = prep(k_raster_follow, rsmem))) return rc;
-        int rgrid = 0;
-        if ((rc = persistent_grid(k_raster_follow, rt, rsmem, kp.E, &rgrid))) return rc;
-        if (rgrid > sms * follow_per_sm) rgrid = sms * follow_per_sm;
-        cudaError_t err = cudaEventRecord(ss.fork, s);
-        if (err == cudaSuccess) err = cudaStreamWaitEvent(ss.stream, ss.fork, 0);
-        if (err != cudaSuccess) return cuda_fail(err, "fork");
-        k_raster_follow<<<rgrid, rt, rsmem, ss.stream>>>(kp, st->x, st->xa, io->grid, io->positions, st->work + 2);
-        if ((rc = check_launch("k_raster_follow"))) return rc;
-        kp.publish = 1;
-    }
+    if ((rc = side_stream(&ss))) return rc;
+    if ((rc = prep(k_raster_follow, follow_smem))) return rc;
+    int rgrid = 0;
+    if ((rc = persistent_grid(k_raster_follow, follow_threads, follow_smem, kp.E, &rgrid))) return rc;
+    if (rgrid > sms * follow_per_sm) rgrid = sms * follow_per_sm;
+    cudaError_t err = cudaEventRecord(ss.fork, s);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(ss.stream, ss.fork, 0);
+    if (err != cudaSuccess) return cuda_fail(err, "fork");
+    kp.publish = 1;
     kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
-    if (follow) {
-        if ((rc = check_launch("swarm_step"))) return rc;
-        cudaError_t err = cudaEventRecord(ss.join, ss.stream);
-        if (err == cudaSuccess) err = cudaStreamWaitEvent(s, ss.join, 0);
-        if (err != cudaSuccess) return cuda_fail(err, "join");
-    }
+    if ((rc = check_launch("swarm_step"))) return rc;
+    k_raster_follow<<<rgrid, follow_threads, follow_smem, ss.stream>>>(kp, st->x, st->xa, io->grid, io->positions,
+                                                                        st->work + 2);
+    if ((rc = check_launch("k_raster_follow"))) return rc;
+    err = cudaEventRecord(ss.join, ss.stream);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(s, ss.join, 0);
+    if (err != cudaSuccess) return cuda_fail(err, "join");
     return check_launch("swarm_step");
 }
 
