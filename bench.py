@@ -36,18 +36,23 @@ A, G = 10, 84
 FLOPS_PER_PAIR = 18
 
 
-def ncu_traffic(kernel="k_step"):
-    """dram read+write bytes per launch of the dominant kernel, from the committed ncu --set full summary."""
+def ncu_traffic(kernels=("k_step", "k_raster_follow")):
+    """dram read+write bytes per batch-step (the step kernel + its concurrent follower), from the committed
+    ncu --set full summary (profiles/rNN_summary.json, newest round)."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     try:
         for name in sorted(os.listdir(pdir)):
             if name.endswith("_summary.json"):
                 with open(os.path.join(pdir, name)) as f:
-                    d = json.load(f).get(kernel, {})
-                if "dram__bytes_read.sum" in d:
-                    unit = 1e6      # ncu prints Mbyte for this kernel
-                    best = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * unit
+                    summ = json.load(f)
+                tot = 0.0
+                for k in kernels:
+                    d = summ.get(k, {})
+                    if "dram__bytes_read.sum" in d:
+                        tot += (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])) * 1e6   # ncu: Mbyte
+                if tot:
+                    best = tot
     except Exception:
         pass
     return best

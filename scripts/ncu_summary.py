@@ -82,7 +82,7 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     summary = {}
-    for kern in ("k_step", "k_forces", "k_rasterize"):
+    for kern in ("k_step", "k_raster_follow", "k_forces", "k_rasterize"):
         rep = os.path.join(OUT, "prof_%s.ncu-rep" % kern)
         if not os.path.isfile(rep):
             continue
@@ -92,7 +92,8 @@ def main():
         mix, hot = source_mix(rep)
         lines = ["# ncu --set full: %s  (%s)" % (kern, d.get("Kernel Name", ("?", ""))[0]), "",
                  "command: `ncu --set full --clock-control none --import-source on -k regex:%s --launch-skip 4 -c 1 "
-                 "python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-graph` (C4: 4096 envs x 256 locusts)" % kern, "",
+                 "python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-graph --no-paac` (C4: 4096 envs x 256 locusts; ncu "
+                 "serialises kernels, so k_step and k_raster_follow -- concurrent in production -- are each seen alone)" % kern, "",
                  "| metric | value | unit |", "|---|---|---|"]
         vals = {}
         for k in KEYS:
