@@ -1,7 +1,8 @@
-// Block-level device code of the swarm hot path (sm_100a).  A CTA works on one env at a time
-// with two warp-specialised thread groups: the FORCE group (dynamics, reward, auto-reset) and
-// the RASTER group (occupancy grid of the env the force group finished last), so that the
-// rasteriser's latency chains and HBM stores run under the next env's force phase:
+// Block-level device code of the swarm hot path (sm_100a).  A CTA works on one env at a time.  The
+// FORCE group (dynamics, reward, auto-reset) and the rasteriser are kept apart so that the
+// rasteriser's latency chains and HBM stores run under another env's force phase: either as a
+// second warp-specialised thread group of the same persistent CTA (RASTER group, small swarms)
+// or as a follower kernel on its own stream (k_raster_follow, large swarms) -- see swarm_b200.cu.
 //   * an env's FP64 integrator state, its frozen noise row and its actions are prefetched
 //     (cp.async) into one of two shared-memory STAGE buffers while the previous env is being
 //     stepped, and stay there for the whole step (step, auto-reset burn-in and rasterise

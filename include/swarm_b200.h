@@ -123,7 +123,9 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
 
 /* SwarmEnv._step (multiagent.py:30-44) + TimeLimit + (optionally) the SwarmRunner._run
  * auto-reset (emulator_runner.py:126-135) and SwarmStateProcessor.process_state
- * (state_processors.py:29-42) of the resulting state, all in one kernel.
+ * (state_processors.py:29-42) of the resulting state: one kernel, or -- for large swarms when
+ * st->work is given -- the step kernel plus a rasteriser kernel that follows it concurrently on
+ * an internal stream (joined back into `stream` before the call returns its work to it).
  * reset_draws: nullable; injected draws used by auto-reset instead of Philox. */
 int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                const SwarmInjectedDraws* reset_draws, swarm_stream_t stream);
