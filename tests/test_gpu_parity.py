@@ -620,3 +620,28 @@ def test_step_under_cuda_graph_replay_equals_eager(M):
     for k in ("x", "xa", "elapsed", "episode", "grid", "positions", "reward", "done_u8"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     assert int(a.episode[0]) == 2
+
+
+@pytest.mark.parametrize("G", [20, 83, 84])
+def test_follower_rasteriser_large_swarm_grid_sizes(M, G):
+    """N >= 160 takes the two-kernel step (k_step + k_raster_follow on the side stream): observations bit-exact vs
+    the oracle for TMA-able and odd grid sizes, over consecutive steps including an auto-reset, and identical to
+    the in-kernel raster warps (work=None)."""
+    E, N = 37, 176
+    a = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes")
+    b = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes")
+    b.state_c.work = None                                    # static assignment, raster warps inside k_step
+    a.reset(); b.reset()
+    rs = np.random.RandomState(G)
+    for t in range(5):
+        act = to_dev(clipped(rs, (E, 10, 2)))
+        a.step(act); b.step(act.clone())
+        torch.cuda.synchronize()
+        assert torch.equal(a.x, b.x) and torch.equal(a.grid, b.grid) and torch.equal(a.positions, b.positions)
+        assert torch.equal(a.done_u8, b.done_u8) and int(a.work.sum()) == 0
+        gx, gxa = a.x.cpu().numpy(), a.xa.cpu().numpy()
+        for e in range(0, E, 6):
+            g, p_ = so.rasterize(gx[e], gxa[e], G)
+            assert np.array_equal(a.grid[e].cpu().numpy(), g.astype(np.float32)), (G, t, e)
+            assert np.array_equal(a.positions[e].cpu().numpy(), p_)
+    assert int(a.episode[0]) == 2
