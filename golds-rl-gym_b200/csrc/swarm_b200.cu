@@ -56,7 +56,7 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
     const int N = kp.N, A = kp.A;
     const int n_all = blockDim.x, n_raster = n_all - n_force;
     const bool raster = n_raster > 0;
-    Smem sm = carve(smem_raw, N, A, kp.G, 2, true, ModeT<MODE>::SYM);
+    Smem sm = carve(smem_raw, N, A, kp.G, kp.n_stage, true, ModeT<MODE>::SYM);
 
     // Env assignment: the first two envs of a CTA are static (blockIdx.x, + gridDim.x); with a work queue the
     // later ones are drawn from an atomic counter (index 2 * gridDim.x + ticket), which evens out the CTAs'
@@ -490,6 +490,7 @@ KP make_kp(const SwarmParams* p) {
     k.n_sms = 1;
     k.dynamic = 0;
     k.publish = 0;
+    k.n_stage = 2;
     return k;
 }
 
@@ -699,14 +700,15 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     const int follow_threads = (kp.N + kp.A) <= 128 ? 32 : 128;
     const size_t follow_smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, true, 0);
     int follow_per_sm = (kp.N + kp.A) <= 128 ? 6 : 2;            // raster CTAs per SM that keep pace with the step
-    while (follow_per_sm > 0 && follow_per_sm * (follow_smem + 1024) + step_smem(p, false) + 1024 > kMaxSmem) --follow_per_sm;
+    while (follow_per_sm > 0 && follow_per_sm * (follow_smem + 1024) + step_smem(p, false, 1) + 1024 > kMaxSmem) --follow_per_sm;
     // Measured (B200, 4096 envs): the follower wins for large swarms (N = 256: 0.181 vs 0.199 ms, N = 192: 0.123 vs
     // 0.135), the in-kernel raster warps for small ones, where the rasteriser -- not the forces -- is the critical path
     // (N = 128: 0.080 vs 0.108 ms, N = 64: 0.052 vs 0.069); N = 160 is the break-even.
     const bool follow = want_grid && st->work != nullptr && kp.N >= 160 && follow_per_sm > 0 &&
                         follow_per_sm * follow_threads + block_threads(kp.N) <= 2048;
     const bool raster = want_grid && !follow;
-    const size_t smem = step_smem(p, raster);
+    kp.n_stage = raster ? 2 : 1;          // one env per CTA (no raster warps): nothing to prefetch into a second buffer
+    const size_t smem = step_smem(p, raster, kp.n_stage);
     const int nf = block_threads(kp.N);
     const int nt = nf + (raster ? raster_threads(kp.N, kp.A) : 0);
     const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;
