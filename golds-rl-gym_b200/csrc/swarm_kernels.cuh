@@ -750,11 +750,18 @@ __device__ __forceinline__ double edge_at(int i, double lo, double hi, double st
     return i >= G ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
 }
 
-// The bin is guessed with a reciprocal multiply and then corrected against the exact edges.
+// The bin is guessed with a reciprocal multiply.  The guess q = (p - lo) / step is within ~1e-13 of the real
+// position of p between numpy's edges (each edge is within 2 ulp of lo + i*step, the subtraction and the
+// multiply add a few ulp more), so a guess whose fractional part is further than 1e-9 from 0 and 1 is certain;
+// anything else -- points on or next to an edge, outside [lo, hi) -- is settled against the exact edges.
 __device__ __forceinline__ int count_le(double p, double lo, double hi, double step, double inv_step, int G) {
-    if (!(p == p)) return G + 1;                 // NaN sorts last
+    if (p == lo) return 1;                       // e[0] = lo exactly (the grounded locusts' y = 0 lands here)
     const double q = (p - lo) * inv_step;
-    int g = q < -1.0 ? -1 : (q > (double)G ? G : (int)floor(q));
+    const double fl = floor(q);
+    const double fr = q - fl;
+    if (q > 0.0 && q < (double)G && fr > 1e-9 && fr < 1.0 - 1e-9) return (int)fl + 1;
+    if (!(p == p)) return G + 1;                 // NaN sorts last
+    int g = q < -1.0 ? -1 : (q > (double)G ? G : (int)fl);
     while (g < G && edge_at(g + 1, lo, hi, step, G) <= p) ++g;
     while (g >= 0 && edge_at(g, lo, hi, step, G) > p) --g;
     return g + 1;                                // #{i in [0,G] : e[i] <= p}
