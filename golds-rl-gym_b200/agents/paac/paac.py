@@ -260,16 +260,23 @@ class GridPAACLearner(object):
         else:
             self._update_body()
 
-    def train(self, max_updates=None, log_every=None):
-        """paac.py:226-406 without the TF session / monitor thread.  Returns the mean frames/s."""
+    def train(self, max_updates=None, log_every=None, monitor=None, eval_every=30.0):
+        """paac.py:226-406 without the TF session.  ``monitor``: a SwarmPolicyMonitor evaluated every
+        ``eval_every`` seconds (the reference does this from a thread, paac.py:277-282; here between updates,
+        on rank 0).  Returns the mean frames/s."""
         self.start()
         counter, start = 0, time.time()
         log_every = log_every or max(1, int(5048 / self.total_emulators))
         global_step_start = self.global_step
         loop_start = time.time()
+        last_eval = time.time()
         while self.global_step < self.max_global_steps and (max_updates is None or counter < max_updates):
             self.update()
             counter += 1
+            if monitor is not None and self.rank == 0 and time.time() - last_eval >= eval_every:
+                torch.cuda.synchronize(self.device)
+                monitor.eval_once(global_step=self.global_step)
+                last_eval = time.time()
             if counter % log_every == 0 and self.rank == 0:
                 torch.cuda.synchronize(self.device)
                 now = time.time()

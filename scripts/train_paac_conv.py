@@ -55,38 +55,47 @@ def get_network_and_environment_creator(args, random_seed=3):
     return network_creator, env_creator
 
 
+# (flags, default, type, dest) -- names and defaults are the reference's (train_paac_conv.py:95-121)
+REFERENCE_FLAGS = [
+    (('-d', '--device'), '/gpu:0', str, 'device'),
+    (('--e',), 0.1, float, 'e'),
+    (('--alpha',), 0.99, float, 'alpha'),
+    (('-lr', '--initial_lr'), 0.0001, float, 'initial_lr'),
+    (('-lra', '--lr_annealing_steps'), 80000000, int, 'lr_annealing_steps'),
+    (('--entropy',), 0.02, float, 'entropy_regularisation_strength'),
+    (('--clip_norm',), 40.0, float, 'clip_norm'),
+    (('--clip_norm_type',), 'global', str, 'clip_norm_type'),
+    (('--gamma',), 0.99, float, 'gamma'),
+    (('--max_global_steps',), 80000000, int, 'max_global_steps'),
+    (('--max_local_steps',), 5, int, 'max_local_steps'),
+    (('--single_life_episodes',), False, bool_arg, 'single_life_episodes'),
+    (('-ec', '--emulator_counts'), 32, int, 'emulator_counts'),
+    (('-ew', '--emulator_workers'), 8, int, 'emulator_workers'),
+    (('-df', '--debugging_folder'), 'logs/', str, 'debugging_folder'),
+    (('-rs', '--random_start'), True, bool_arg, 'random_start'),
+    (('--scale',), 1000., float, 'scale'),
+    (('--height',), 84, int, 'height'),
+    (('--filters',), 32, int, 'filters'),
+    (('--rnn-length',), 5, int, 'rnn_length'),
+    (('--static-size',), 2, int, 'static_size'),
+    (('--temporal-size',), 2, int, 'temporal_size'),
+    (('--static-hidden-size',), 32, int, 'static_hidden_size'),
+    (('--temporal-hidden-size',), 32, int, 'temporal_hidden_size'),
+]
+
+
 def get_arg_parser():
-    parser = argparse.ArgumentParser()
-    parser.add_argument('-d', '--device', default='/gpu:0', type=str, dest="device")
-    parser.add_argument('--e', default=0.1, type=float, dest="e")
-    parser.add_argument('--alpha', default=0.99, type=float, dest="alpha")
-    parser.add_argument('-lr', '--initial_lr', default=0.0001, type=float, dest="initial_lr")
-    parser.add_argument('-lra', '--lr_annealing_steps', default=80000000, type=int, dest="lr_annealing_steps")
-    parser.add_argument('--entropy', default=0.02, type=float, dest="entropy_regularisation_strength")
-    parser.add_argument('--clip_norm', default=40.0, type=float, dest="clip_norm")
-    parser.add_argument('--clip_norm_type', default="global", dest="clip_norm_type")
-    parser.add_argument('--gamma', default=0.99, type=float, dest="gamma")
-    parser.add_argument('--max_global_steps', default=80000000, type=int, dest="max_global_steps")
-    parser.add_argument('--max_local_steps', default=5, type=int, dest="max_local_steps")
-    parser.add_argument('--single_life_episodes', default=False, type=bool_arg, dest="single_life_episodes")
-    parser.add_argument('-ec', '--emulator_counts', default=32, type=int, dest="emulator_counts")
-    parser.add_argument('-ew', '--emulator_workers', default=8, type=int, dest="emulator_workers")
-    parser.add_argument('-df', '--debugging_folder', default='logs/', type=str, dest="debugging_folder")
-    parser.add_argument('-rs', '--random_start', default=True, type=bool_arg, dest="random_start")
-    parser.add_argument('--scale', default=1000., type=float)
-    parser.add_argument('--height', default=84, type=int)
-    parser.add_argument('--filters', default=32, type=int)
-    parser.add_argument('--rnn-length', default=5, type=int)
-    parser.add_argument('--static-size', default=2, type=int)
-    parser.add_argument('--temporal-size', default=2, type=int)
-    parser.add_argument('--static-hidden-size', default=32, type=int)
-    parser.add_argument('--temporal-hidden-size', default=32, type=int)
-    # additions
+    parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    for flags, default, kind, dest in REFERENCE_FLAGS:
+        parser.add_argument(*flags, default=default, type=kind, dest=dest)
+    # additions of this implementation
     parser.add_argument('--n_locusts', default=None, type=int, help="SwarmEnv.N_LOCUSTS (default 80)")
     parser.add_argument('--max_updates', default=None, type=int)
     parser.add_argument('--no_cuda_graph', action='store_true')
     parser.add_argument('--reward_indexing', default='reference', choices=['reference', 'per_agent'])
     parser.add_argument('--mask_terminals', action='store_true')
+    parser.add_argument('--eval_every', default=30.0, type=float,
+                        help="seconds between evaluation episodes on Swarm-eval-v0 (policy_monitor.py); 0 = off")
     parser.add_argument('--obs', default='auto', choices=['auto', 'compact', 'expanded'],
                         help="observation the net consumes: compact = (grid, positions) with conv1 factorised")
     return parser
@@ -114,7 +123,15 @@ def main(args):
         sys.exit(0)
     signal.signal(signal.SIGINT, on_signal)
     signal.signal(signal.SIGTERM, on_signal)
-    fps = learner.train(max_updates=args.max_updates)
+    monitor = None
+    if args.eval_every > 0 and int(os.environ.get("RANK", "0")) == 0:
+        os.makedirs(args.debugging_folder, exist_ok=True)
+        pm = pkg.submodule("agents.paac.policy_monitor")
+        sp = pkg.submodule("agents.state_processors")
+        monitor = pm.SwarmPolicyMonitor(global_policy_net=learner.network,
+                                        state_processor=sp.SwarmStateProcessor(grid_size=args.height),
+                                        out_dir=args.debugging_folder)
+    fps = learner.train(max_updates=args.max_updates, monitor=monitor, eval_every=args.eval_every)
     if int(os.environ.get("RANK", "0")) == 0:
         logging.info("done: %d global steps, %.1f frames/s", learner.global_step, fps)
     learner.cleanup()
