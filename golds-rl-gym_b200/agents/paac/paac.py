@@ -50,6 +50,7 @@ class GridPAACLearner(object):
         # compact_obs: the net consumes (grid (E,G,G,2), positions (E,A,2)) through forward_compact -- exactly the
         # same function of the observation, without ever materialising the reference's (E,A,G,G,3) layout
         self._compact_request = compact_obs
+        torch.backends.cudnn.benchmark = True       # fixed shapes: let cuDNN pick its fastest algorithms once
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
