@@ -33,7 +33,7 @@ class GridPAACLearner(object):
 
     def __init__(self, network_creator, environment_creator, args, emulator_class=SwarmRunner, state_processor=None,
                  device=None, reward_indexing="reference", mask_terminals=False, use_cuda_graph=True,
-                 compact_obs="auto"):
+                 compact_obs="auto", net_precision="fp32"):
         self.args = args
         self.emulator_class = emulator_class
         self.max_local_steps = args.max_local_steps
@@ -51,6 +51,13 @@ class GridPAACLearner(object):
         # same function of the observation, without ever materialising the reference's (E,A,G,G,3) layout
         self._compact_request = compact_obs
         torch.backends.cudnn.benchmark = True       # fixed shapes: let cuDNN pick its fastest algorithms once
+        # net_precision: "fp32" = PyTorch defaults (FP32 dense layers, cuDNN convolutions may use TF32), "tf32" also lets
+        # the dense layers use TF32 tensor cores, "bf16" runs forward/backward under autocast (FP32 master weights).
+        if net_precision not in ("fp32", "tf32", "bf16"):
+            raise ValueError("net_precision must be fp32, tf32 or bf16")
+        self.net_precision = net_precision
+        if net_precision == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -119,10 +126,16 @@ class GridPAACLearner(object):
         mu, sigma, v = out["mu"], out["sigma"], out["vs"]
         return mu + sigma * torch.randn_like(mu), v
 
+    def _autocast(self):
+        return torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.net_precision == "bf16")
+
     def _predict(self, t):
-        if self.compact_obs:
-            return self.network.predict_compact(self.grids[t], self.positions[t])
-        return self.network.predict(self.states[t].view(self.real_batch_size, *self.states.shape[3:]))
+        with self._autocast():
+            if self.compact_obs:
+                out = self.network.predict_compact(self.grids[t], self.positions[t])
+            else:
+                out = self.network.predict(self.states[t].view(self.real_batch_size, *self.states.shape[3:]))
+        return {k: v.float() for k, v in out.items()}
 
     def _rollout_step(self, t):
         E, A = self.emulator_counts, self.N_AGENTS
@@ -169,8 +182,9 @@ class GridPAACLearner(object):
             obs, pos = self.grids[:T].view(T * E, *self.grids.shape[2:]), self.positions[:T].view(T * E, A, 2)
         else:
             obs, pos = self.states[:T].view(T * B, *self.states.shape[3:]), None
-        out = self.network.losses(obs, self.actions.view(T * B, self.num_actions),
-                                  self.adv_batch.view(-1) / self.network.scale, self.y_batch.view(-1), positions=pos)
+        with self._autocast():
+            out = self.network.losses(obs, self.actions.view(T * B, self.num_actions),
+                                      self.adv_batch.view(-1) / self.network.scale, self.y_batch.view(-1), positions=pos)
         self.flat_grad.zero_()
         out["loss"].backward()
         sharding.allreduce_mean_(self.flat_grad)

@@ -91,7 +91,7 @@ class ConvSingleAgentPolicyNetwork(nn.Module):
                 ok = (oh >= 0) & (oh < OH) & (ow >= 0) & (ow < OW) & (kh < k) & (kw < k)
                 tap = w_hot[:, (kh.clamp(max=k - 1) * k + kw.clamp(max=k - 1))].t() * ok[:, None].to(w_hot.dtype)   # (B,32)
                 idx = (oh.clamp(0, OH - 1) * OW + ow.clamp(0, OW - 1))[:, None, None].expand(-1, 1, F1)
-                x.scatter_add_(1, idx, tap[:, None, :])
+                x.scatter_add_(1, idx, tap[:, None, :].to(x.dtype))
         x = F.relu_(x).view(E * A, OH, OW, F1).permute(0, 3, 1, 2)       # channels_last (B,32,oh,ow), no copy
         return self._trunk_and_heads(x)
 

@@ -96,6 +96,8 @@ def get_arg_parser():
     parser.add_argument('--mask_terminals', action='store_true')
     parser.add_argument('--eval_every', default=30.0, type=float,
                         help="seconds between evaluation episodes on Swarm-eval-v0 (policy_monitor.py); 0 = off")
+    parser.add_argument('--net_precision', default='fp32', choices=['fp32', 'tf32', 'bf16'],
+                        help="policy net arithmetic (the reference trains in FP32)")
     parser.add_argument('--obs', default='auto', choices=['auto', 'compact', 'expanded'],
                         help="observation the net consumes: compact = (grid, positions) with conv1 factorised")
     return parser
@@ -116,7 +118,8 @@ def main(args):
     paac = pkg.submodule("agents.paac.paac")
     learner = paac.GridPAACLearner(network_creator, env_creator, args, reward_indexing=args.reward_indexing,
                                    mask_terminals=args.mask_terminals, use_cuda_graph=not args.no_cuda_graph,
-                                   compact_obs={"auto": "auto", "compact": True, "expanded": False}[args.obs])
+                                   compact_obs={"auto": "auto", "compact": True, "expanded": False}[args.obs],
+                                   net_precision=args.net_precision)
 
     def on_signal(signum, frame):            # train_paac_conv.py:47-58
         learner.cleanup()
