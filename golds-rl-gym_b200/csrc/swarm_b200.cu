@@ -699,7 +699,8 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     // The follower spins until the step publishes an env, so the step must always be able to get onto an SM next to it.
     const int follow_threads = (kp.N + kp.A) <= 128 ? 32 : 128;
     const size_t follow_smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, true, 0);
-    int follow_per_sm = (kp.N + kp.A) <= 128 ? 6 : 2;            // raster CTAs per SM that keep pace with the step
+    // raster CTAs per SM that keep pace with the step (measured at 4096 envs: N = 160: 4 -> 0.110 ms, 2 -> 0.118; N = 192 and up: 2)
+    int follow_per_sm = (kp.N + kp.A) <= 128 ? 6 : (kp.N < 192 ? 4 : 2);
     while (follow_per_sm > 0 && follow_per_sm * (follow_smem + 1024) + step_smem(p, false, 1) + 1024 > kMaxSmem) --follow_per_sm;
     // Measured (B200, 4096 envs): the follower wins for large swarms (N = 256: 0.181 vs 0.199 ms, N = 192: 0.123 vs
     // 0.135), the in-kernel raster warps for small ones, where the rasteriser -- not the forces -- is the critical path
