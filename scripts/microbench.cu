@@ -65,6 +65,31 @@ __global__ void k_pipe2(float* out, float seed) {
     if (s == 123.456f) out[0] = s;
 }
 
+// FP64 -> FP32 conversion: which pipe?  OP 0: DADD + cvt.rn.f32.f64 chain; OP 1: MUFU.EX2 chain; OP 2: both interleaved
+template <int OP>
+__global__ void k_cvt(float* out, double seed) {
+    double d[CHAINS];
+    float f[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) { d[c] = seed + 0.001 * (threadIdx.x + c); f[c] = 0.5f + 0.001f * c; }
+    for (int i = 0; i < ITERS / 4; ++i) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; ++c) {
+            if (OP == 0 || OP == 2) {
+                float t;
+                asm volatile("cvt.rn.f32.f64 %0, %1;" : "=f"(t) : "d"(d[c]));
+                d[c] = __dadd_rn(d[c], (double)1e-9);
+                f[c] += t * 1e-30f;
+            }
+            if (OP == 1 || OP == 2) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f[c]));
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += f[c] + (float)d[c];
+    if (s == 123.456f) out[0] = s;
+}
+
 template <int OP>
 __global__ void k_pipe64(double* out, double seed) {
     double v[CHAINS];
@@ -160,6 +185,17 @@ int main() {
         ms = time_ms([&] { k_pipe2<1><<<blocks, threads>>>(out, 0.5f); });
         per_s = (double)blocks * threads * ITERS * CHAINS / (ms * 1e-3);
         printf("{\"bench\": \"fadd2\", \"ms\": %.4f, \"thread_inst_per_s\": %.4e, \"inst_per_clk_per_sm_at_1965MHz\": %.2f}\n", ms, per_s, per_s / sms / 1.965e9);
+    }
+    {
+        const int blocks = sms * 8, threads = 256;
+        const char* nm[] = {"cvt_f32_f64+dadd", "mufu_ex2_quarter", "cvt_f32_f64+dadd+mufu_ex2"};
+        for (int op = 0; op < 3; op += 2) {
+            float ms = 0;
+            if (op == 0) ms = time_ms([&] { k_cvt<0><<<blocks, threads>>>(out, 0.5); });
+            if (op == 2) ms = time_ms([&] { k_cvt<2><<<blocks, threads>>>(out, 0.5); });
+            const double per_s = (double)blocks * threads * (ITERS / 4) * CHAINS / (ms * 1e-3);
+            printf("{\"bench\": \"%s\", \"ms\": %.4f, \"iters_per_clk_per_sm_at_1965MHz\": %.2f}\n", nm[op], ms, per_s / sms / 1.965e9);
+        }
     }
     {
         double* d;
