@@ -609,6 +609,19 @@ int check_launch(const char* what) {
         default: { constexpr int TT = 4; __VA_ARGS__; } break; \
     }
 
+// swarm_step_host keeps the launches of its last argument set as an instantiated graph
+struct HostStepKey {
+    SwarmParams p;
+    SwarmState st;
+    SwarmStepIO io;
+    int device;
+};
+struct HostStepGraph {
+    HostStepKey key;
+    cudaGraphExec_t exec = nullptr;
+};
+constexpr int kHostGraphs = 32;     // distinct (params, state, buffers) argument sets kept per host thread
+
 // device-visible alias of a pinned (page-locked, UVA-mapped) host pointer, or nullptr
 template <typename T>
 T* mapped_host(T* host) {
@@ -771,6 +784,56 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
         direct.actions_f32 = d_act;
         direct.reward = d_rew;
         direct.done = d_done;
+        // The same call repeats every step with the same buffers: keep its launches (step kernel, and for large
+        // swarms fork -> follower -> join on the side stream) as ONE instantiated CUDA graph per argument set.
+        // UseNodePriority matters: the follower only runs NEXT TO the step if its kernel node keeps the side
+        // stream's higher priority (with equal priorities the step's CTAs are all dispatched first: 0.255 vs 0.189 ms).
+        static thread_local HostStepGraph cache_entries[kHostGraphs];
+        static thread_local unsigned next_victim = 0;
+        HostStepKey key;
+        memset(&key, 0, sizeof(key));
+        key.p = *p; key.st = *st; key.io = direct;
+        if (cudaGetDevice(&key.device) != cudaSuccess) key.device = -1;
+        cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s, &capturing);
+        if (capturing == cudaStreamCaptureStatusNone && key.device >= 0) {
+            HostStepGraph* hit = nullptr;
+            for (int i = 0; i < kHostGraphs; ++i)
+                if (cache_entries[i].exec && memcmp(&cache_entries[i].key, &key, sizeof(key)) == 0) hit = &cache_entries[i];
+            if (!hit) {
+                HostStepGraph& cached = cache_entries[next_victim++ % kHostGraphs];      // round-robin replacement
+                if (cached.exec) { cudaGraphExecDestroy(cached.exec); cached.exec = nullptr; }
+                // one plain call first: it warms the per-kernel caches (attribute / occupancy queries are not
+                // capturable) and is itself this step
+                const int rc = swarm_step(p, st, &direct, nullptr, stream);
+                if (rc) return rc;
+                err = cudaStreamSynchronize(s);
+                if (err != cudaSuccess) return cuda_fail(err, "stream sync");
+                cudaStream_t cap = nullptr;
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess) {
+                    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                        const int rc2 = swarm_step(p, st, &direct, nullptr, (swarm_stream_t)cap);
+                        const cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
+                        if (rc2 == SWARM_OK && e2 == cudaSuccess && graph &&
+                            cudaGraphInstantiateWithFlags(&cached.exec, graph, cudaGraphInstantiateFlagUseNodePriority) == cudaSuccess) {
+                            cached.key = key;
+                        } else {
+                            cached.exec = nullptr;
+                        }
+                        if (graph) cudaGraphDestroy(graph);
+                    }
+                    cudaStreamDestroy(cap);
+                }
+                cudaGetLastError();       // a failed capture must not poison later calls: the plain path still works
+                return SWARM_OK;
+            }
+            err = cudaGraphLaunch(hit->exec, s);
+            if (err != cudaSuccess) return cuda_fail(err, "cudaGraphLaunch");
+            err = cudaStreamSynchronize(s);
+            if (err != cudaSuccess) return cuda_fail(err, "stream sync");
+            return SWARM_OK;
+        }
         const int rc = swarm_step(p, st, &direct, nullptr, stream);
         if (rc) return rc;
         err = cudaStreamSynchronize(s);

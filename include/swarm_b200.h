@@ -126,6 +126,9 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
  * (state_processors.py:29-42) of the resulting state: one kernel, or -- for large swarms when
  * st->work is given -- the step kernel plus a rasteriser kernel that follows it concurrently on
  * an internal stream (joined back into `stream` before the call returns its work to it).
+ * The call can be captured into a CUDA graph; instantiate such a graph with
+ * cudaGraphInstantiateFlagUseNodePriority (PyTorch does), or the follower loses its priority
+ * and runs after the step instead of next to it.
  * reset_draws: nullable; injected draws used by auto-reset instead of Philox. */
 int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                const SwarmInjectedDraws* reset_draws, swarm_stream_t stream);
