@@ -68,7 +68,9 @@ def peaks():
 
 
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from BEFORE the warm-up (it needs ~0.2 s to start); only the samples whose
+    timestamps fall inside the timed region count."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -82,6 +84,7 @@ class ClockSampler(object):
             self.proc = None
 
     def stop(self, t_begin, t_end):
+        import datetime
         if self.proc is None:
             return None
         time.sleep(0.06)
@@ -91,23 +94,28 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
             return None
-        sm, mx, reasons = [], 0.0, set()
+        rows, mx = [], 0.0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
             f = [s.strip() for s in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
+                mx = max(mx, float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not rows:
             return None
-        busy = sorted(sm)[len(sm) // 2:]        # the upper half of the samples = under load
-        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t_begin - 0.02 <= r[0] <= t_end + 0.02]
+        where = "timed region"
+        if not inside:                      # region shorter than the polling period: fall back to the busiest samples
+            inside = sorted(rows, key=lambda r: r[1])[len(rows) // 2:]
+            where = "whole run (timed region shorter than the 20 ms polling period)"
+        reasons = sorted({n for r in inside for n in r[2]})
+        return dict(sm_mhz=statistics.median([r[1] for r in inside]), sm_max_mhz=mx, reasons=reasons,
+                    samples=len(inside), sampled="nvidia-smi -lms 20, " + where)
 
 
 def run_reference(args, wl):
@@ -258,6 +266,7 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes a moment to come up
     step = lambda i: env.step(ring[i & 7])
     for i in range(W):
         step(i)
@@ -277,7 +286,6 @@ def main():
             for i in range(8):
                 step(i)
         K = ((K + 7) // 8) * 8
-    sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
     if graph is not None:
         ms = timed(lambda i: graph.replay(), K // 8)
