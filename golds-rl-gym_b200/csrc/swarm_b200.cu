@@ -487,7 +487,6 @@ KP make_kp(const SwarmParams* p) {
     k.eps_s = (float)(1e-6 * 1.4426950408889634);  // multiagent.py:103 "+ 0.000001", scaled
     k.key = make_uint2((uint32_t)(p->seed & 0xffffffffu), (uint32_t)(p->seed >> 32));
     k.env_off = (uint32_t)p->env_id_offset;
-    k.n_sms = 1;
     k.dynamic = 0;
     k.publish = 0;
     k.n_stage = 2;
@@ -732,7 +731,6 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if ((rc = prep(kernel, smem))) return rc;
     int grid = 0, sms = 1;
     if ((rc = persistent_grid(kernel, nt, smem, kp.E, &grid, &sms))) return rc;
-    kp.n_sms = sms > 0 ? sms : 1;
     // without raster warps to overlap there is nothing to gain from persistence, and hardware-scheduled one-env
     // CTAs measure 8 % faster (C4: 0.154 vs 0.166 ms)
     if (!raster) grid = kp.E;

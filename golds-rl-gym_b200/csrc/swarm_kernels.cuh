@@ -46,7 +46,6 @@ struct KP {
     float F, nInvL, U, Gv, eps_s;
     uint2 key;
     uint32_t env_off;
-    int n_sms;        // SMs of the device
     int dynamic;      // k_step: draw the third and later envs of a CTA from the work queue (SwarmState::work)
     int n_stage;      // k_step: stage buffers in shared memory (2 = prefetch the CTA's next env, 1 = one env per CTA)
     int publish;      // k_step: raise work[2 + e] once env e's new state is in memory (k_raster_follow waits for it)
