@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + sorted(PAAC))
     ap.add_argument("--math", default="fast", choices=["fast", "precise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary C2 figure (1024 envs x 64 locusts)")
     ap.add_argument("--no-paac", action="store_true", help="skip the secondary PAAC frames/s figure (config 3)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU-baseline sample")
@@ -356,6 +357,18 @@ def main():
         except Exception as exc:      # the secondary figure must never take the headline down
             paac = {"error": repr(exc)}
 
+    # BASELINE.json configs[1] (C2) next to the headline workload: measured by a child process of this very script
+    secondary = None
+    if world == 1 and rank == 0 and args.workload == "c4" and not args.no_secondary:
+        try:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c2", "--steps", "512", "--warmup",
+                                  str(W), "--no-cpu-baseline", "--no-paac", "--no-secondary"], capture_output=True, text=True,
+                                 timeout=300)
+            d = json.loads(res.stdout.strip().splitlines()[-1])
+            secondary = {"c2": {k: d[k] for k in ("value", "unit", "ms_per_step", "env_steps_per_sec", "e2e", "config")}}
+        except Exception as exc:
+            secondary = {"c2": {"error": repr(exc)}}
+
     if rank == 0:
         out = {
             "metric": "locust_updates_per_sec", "value": env_steps * N, "unit": "locust-updates/s",
@@ -365,8 +378,10 @@ def main():
                        "envs_per_gpu": E, "n_locusts": N, "n_agents": A, "grid": G, "math": args.math,
                        "actions": "N(0,1) clipped to unit norm, 8 pre-generated device tensors",
                        "launch": "python per step" if args.no_graph else "CUDA graph of 8 steps replayed",
-                       "l2": "no explicit flush: each step streams %.0f MB of observations (> 126 MB L2 for c4)"
-                             % (E * G * G * 2 * 4 / 1e6),
+                       "l2": ("no explicit flush: each step streams %.0f MB of observations, more than the 126 MB L2"
+                              if E * G * G * 8 > 126e6 else
+                              "no explicit flush: each step streams %.0f MB of observations (smaller than the 126 MB L2, "
+                              "which may absorb part of the write-back: secondary figure only)") % (E * G * G * 2 * 4 / 1e6),
                        "parallelism": "env-sharded x%d, no collective" % world},
             "env_steps_per_sec": env_steps, "pairs_per_sec": env_steps * N * (N + A),
             "roofline": {"bound": "fp32", "kernel": "k_step (fused step + rasterise)", "achieved": achieved, "peak": fp32_peak,
@@ -400,6 +415,8 @@ def main():
             out["cpu_baseline"] = cpu
         if paac is not None:
             out["paac"] = paac
+        if secondary is not None:
+            out["secondary"] = secondary
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -15,10 +15,10 @@ timeout 600 python bench.py --workload c2 > gpurun_out/bench_c2.log 2>&1; echo "
 tail -1 gpurun_out/bench_c2.log
 if [ "${1:-}" != "noprof" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-graph --no-paac > gpurun_out/ncu_launches.log 2>&1
+    python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-graph --no-paac --no-secondary > gpurun_out/ncu_launches.log 2>&1
 for k in k_step k_raster_follow k_forces k_rasterize; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 4 -c 1 -f \
-      -o gpurun_out/prof_$k python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-graph --no-paac > gpurun_out/ncu_$k.log 2>&1
+      -o gpurun_out/prof_$k python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-graph --no-paac --no-secondary > gpurun_out/ncu_$k.log 2>&1
   echo "ncu $k rc=$?"
 done
 fi
