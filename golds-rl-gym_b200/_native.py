@@ -5,6 +5,7 @@ sizes go across, torch only provides device memory and the current stream.  Ther
 fallback: if the library is missing and cannot be built, importing the env classes raises.
 """
 import ctypes
+import hashlib
 import os
 import shutil
 import subprocess
@@ -23,16 +24,20 @@ c_void_p, c_int, c_int32, c_int64, c_uint32, c_uint64, c_double, c_float = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64,
     ctypes.c_double, ctypes.c_float)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 SWARM_STEP_AUTO_RESET = 1
 SWARM_STEP_CLIP_ACTIONS = 2
 SWARM_STEP_ACTIONS_F64 = 4
+SWARM_STEP_NO_ACTION_WIND = 8
+SWARM_STEP_INKERNEL_RASTER = 16
+# SwarmParams.tuning: bits 0-2 warps per 64-locust super-tile (0 auto / 1 / 2 / 4), bits 4-5 rasteriser placement
+TUNE_RASTER_FOLLOW, TUNE_RASTER_WARPS, TUNE_RASTER_SELF = 1 << 4, 2 << 4, 3 << 4
 
 
 class SwarmParams(ctypes.Structure):
     _fields_ = [("n_envs", c_int32), ("n_locusts", c_int32), ("n_agents", c_int32), ("grid_size", c_int32),
                 ("n_burn_in", c_int32), ("max_episode_steps", c_int32), ("math_mode", c_int32),
-                ("reserved", c_int32),
+                ("tuning", c_int32),
                 ("noise", c_double), ("gravity", c_double), ("wind", c_double), ("F", c_double),
                 ("L", c_double), ("dt", c_double), ("box_width", c_double), ("box_height", c_double),
                 ("seed", c_uint64), ("env_id_offset", c_int64)]
@@ -40,7 +45,7 @@ class SwarmParams(ctypes.Structure):
 
 class SwarmState(ctypes.Structure):
     _fields_ = [("x", c_void_p), ("xa", c_void_p), ("noise_x", c_void_p), ("noise_a", c_void_p),
-                ("elapsed", c_void_p), ("episode", c_void_p), ("work", c_void_p)]
+                ("elapsed", c_void_p), ("episode", c_void_p), ("work", c_void_p), ("work_words", c_uint64)]
 
 
 class SwarmInjectedDraws(ctypes.Structure):
@@ -64,7 +69,9 @@ SYMBOLS = {
     "swarm_reset": (c_int, [_P(SwarmParams), _P(SwarmState), c_void_p, _P(SwarmInjectedDraws), c_void_p]),
     "swarm_step": (c_int, [_P(SwarmParams), _P(SwarmState), _P(SwarmStepIO), _P(SwarmInjectedDraws), c_void_p]),
     "swarm_step_host": (c_int, [_P(SwarmParams), _P(SwarmState), _P(SwarmStepIO), c_void_p, c_void_p, c_void_p,
-                                c_void_p]),
+                                c_void_p, c_void_p, c_void_p]),
+    "swarm_step_host_clear": (None, []),
+    "swarm_debug_trace": (None, [c_void_p, c_int64]),
     "swarm_rasterize": (c_int, [_P(SwarmParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "swarm_expand_obs": (c_int, [_P(SwarmParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "swarm_forces": (c_int, [_P(SwarmParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -88,11 +95,32 @@ class SwarmNativeError(RuntimeError):
     pass
 
 
-def needs_build():
-    if not os.path.isfile(LIB_PATH):
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp_path(lib_path):
+    return lib_path + ".srchash"
+
+
+def _is_stale(lib_path, sources):
+    """A library is current iff it sits next to a stamp holding the SHA-256 of the sources it was built from
+    (content, not mtimes: the snapshot that carries the built .so to the GPU box does not preserve them)."""
+    if not os.path.isfile(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in SOURCES + [HEADER] if os.path.isfile(s))
+    try:
+        with open(_stamp_path(lib_path)) as f:
+            return f.read().strip() != _digest(sources)
+    except OSError:
+        return True
+
+
+def needs_build():
+    return _is_stale(LIB_PATH, SOURCES + [HEADER])
 
 
 def build(force=False, verbose=False):
@@ -109,6 +137,7 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd))
+    digest = _digest(SOURCES + [HEADER])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         if os.path.exists(tmp):
@@ -117,22 +146,19 @@ def build(force=False, verbose=False):
     if verbose:
         print(res.stderr)
     os.replace(tmp, LIB_PATH)
+    with open(_stamp_path(LIB_PATH), "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 
 def load():
-    """Load the C-ABI library (building it first if the sources are newer and nvcc exists)."""
+    """Load the C-ABI library, building it first if it is missing or was built from other sources.  A library
+    that is stale and cannot be rebuilt is an ERROR (running old kernels silently is worse than not running)."""
     global _lib
     if _lib is not None:
         return _lib
     if needs_build():
-        try:
-            build()
-        except SwarmNativeError:
-            if not os.path.isfile(LIB_PATH):
-                raise
-    if not os.path.isfile(LIB_PATH):
-        raise SwarmNativeError("libswarm_b200.so is missing (%s) and there is no CPU fallback" % LIB_PATH)
+        build()                         # raises SwarmNativeError: no compiler, or the compile failed
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported
@@ -156,10 +182,7 @@ def check(status, what="swarm call"):
 # ------------------------------------------------------------------------------------------------
 # The same C ABI exposed as a PyTorch extension (csrc/torch_binding.cpp -> torch.ops.swarm_b200.*)
 def torch_ext_needs_build():
-    if not os.path.isfile(TORCH_LIB_PATH):
-        return True
-    t = os.path.getmtime(TORCH_LIB_PATH)
-    return any(os.path.isfile(s) and os.path.getmtime(s) > t for s in (TORCH_SOURCE, HEADER))
+    return _is_stale(TORCH_LIB_PATH, [TORCH_SOURCE, HEADER])
 
 
 def build_torch_ext(force=False):
@@ -181,12 +204,15 @@ def build_torch_ext(force=False):
         cmd += ["-L" + lp, "-Wl,-rpath," + lp]
     cmd += ["-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda", "-L" + _PKG_DIR, "-l:libswarm_b200.so",
             "-Wl,-rpath,$ORIGIN"]
+    digest = _digest([TORCH_SOURCE, HEADER])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         if os.path.exists(tmp):
             os.remove(tmp)
         raise SwarmNativeError("g++ failed:\n%s\n%s" % (res.stdout, res.stderr))
     os.replace(tmp, TORCH_LIB_PATH)
+    with open(_stamp_path(TORCH_LIB_PATH), "w") as f:
+        f.write(digest + "\n")
     return TORCH_LIB_PATH
 
 
@@ -198,11 +224,7 @@ def load_torch_ops():
     import torch
     load()                                  # libswarm_b200.so first: the extension links against it
     if torch_ext_needs_build():
-        try:
-            build_torch_ext()
-        except SwarmNativeError:
-            if not os.path.isfile(TORCH_LIB_PATH):
-                raise
+        build_torch_ext()                   # raises when the stale extension cannot be rebuilt
     torch.ops.load_library(TORCH_LIB_PATH)
     if int(torch.ops.swarm_b200.abi_version()) != ABI_VERSION:
         raise SwarmNativeError("torch extension ABI version mismatch")

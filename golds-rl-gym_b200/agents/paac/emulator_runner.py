@@ -37,7 +37,7 @@ class SwarmRunner(object):
         if out is None:
             out = torch.empty(E, A, G, G, 3, dtype=torch.float32, device=state.device)
         p = nat.SwarmParams(n_envs=E, n_locusts=1, n_agents=A, grid_size=G, n_burn_in=0, max_episode_steps=0,
-                            math_mode=0, reserved=0, noise=0, gravity=0, wind=0, F=0, L=1, dt=0, box_width=3.0,
+                            math_mode=0, tuning=0, noise=0, gravity=0, wind=0, F=0, L=1, dt=0, box_width=3.0,
                             box_height=3.0, seed=0, env_id_offset=0)
         nat.check(lib.swarm_expand_obs(ctypes.byref(p), ctypes.c_void_p(state.data_ptr()),
                                        ctypes.c_void_p(agent_positions.data_ptr()), ctypes.c_void_p(out.data_ptr()),

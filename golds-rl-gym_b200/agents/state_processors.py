@@ -27,7 +27,7 @@ class SwarmStateProcessor(object):
 
     def _params(self, n_points, n_agents):
         return nat.SwarmParams(n_envs=1, n_locusts=n_points, n_agents=n_agents, grid_size=self.grid_size,
-                               n_burn_in=10, max_episode_steps=0, math_mode=0, reserved=0, noise=1e-4,
+                               n_burn_in=10, max_episode_steps=0, math_mode=0, tuning=0, noise=1e-4,
                                gravity=-1.0, wind=1.0, F=0.5, L=10.0, dt=0.05, box_width=self.WIDTH,
                                box_height=self.HEIGHT, seed=0, env_id_offset=0)
 

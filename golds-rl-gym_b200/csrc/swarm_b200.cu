@@ -55,8 +55,9 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = kp.N, A = kp.A;
     const int n_all = blockDim.x, n_raster = n_all - n_force;
-    const bool raster = n_raster > 0;
-    Smem sm = carve(smem_raw, N, A, kp.G, kp.n_stage, true, ModeT<MODE>::SYM);
+    const bool raster = n_raster > 0;              // a raster GROUP rides along (kp.raster == 1)
+    const bool self_raster = kp.raster == 2;       // the force group rasterises its own env after the step
+    Smem sm = carve(smem_raw, N, A, kp.G, kp.n_stage, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, kp.raster);
 
     // Env assignment: the first two envs of a CTA are static (blockIdx.x, + gridDim.x); with a work queue the
     // later ones are drawn from an atomic counter (index 2 * gridDim.x + ticket), which evens out the CTAs'
@@ -70,20 +71,37 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
         int e = blockIdx.x, e1 = blockIdx.x + gridDim.x;   // the env of this iteration and of the next one
         if (e < kp.E) prefetch_env(stage_at(smem_raw, N, A, 0), kp, st, io, e, g);
         cp_async_commit();
+        const int cells = kp.G * kp.G;
+        const bool tma = self_raster && tma_zero_fill_ok(io.grid, cells);
+        const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
+        if (self_raster) raster_table_clear(sm, (int)(table_bytes / 4), g);
         int it = 0;
+        if (g.tid == 0) trace_mark(kp, blockIdx.x, TR_ENTRY);
         for (; e < kp.E; ++it) {
+            if (self_raster) {
+                // The observation is ~99 % zeros: they stream out under the whole force phase (TMA bulk stores fed from
+                // the clean counter table, else plain stores); the non-zero cells are scattered over them afterwards.
+                g.sync();                          // the table is clean (first env: just cleared; later: env_raster's exit)
+                float* grid_e = io.grid + (size_t)e * cells * 2;
+                if (tma) {
+                    if (g.tid == 0) tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
+                } else {
+                    raster_zero_fill(grid_e, cells, g.tid, g.n);
+                }
+            }
             int grabbed = 0;                       // the env after next: asked for now, needed an iteration later
             if (dyn && g.tid == 0) grabbed = 2 * (int)gridDim.x + (int)atomicAdd(work, 1u);
             sm.st = stage_at(smem_raw, N, A, it & 1);
             cp_async_wait_all();
             g.sync();      // this env's stage buffer has landed; the other one and sm.nx are free again
+            if (it == 0 && g.tid == 0) trace_mark(kp, blockIdx.x, TR_LOADED);
             if (dyn && it > 0) e1 = sm.mail[1];
             {   // this env's locust noise row: each thread fetches the rows of its own targets, so that its
                 // own wait (before the integration) is all the synchronisation it needs
                 const double2* gnx = reinterpret_cast<const double2*>(io.noise_x ? io.noise_x : st.noise_x) + (size_t)e * N;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    const int j = target_index<MODE>(g, t);
+                    const int j = target_index<MODE>(g, t, kp);
                     if (j < N) cp_async<16>(sm.nx + j, gnx + j);
                 }
                 cp_async_commit();
@@ -130,7 +148,10 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             int r = -1;                              // -1: the step proper; >= 0: burn-in row being stepped
             float* v_out = io.v_out ? io.v_out + (size_t)e * N * 2 : nullptr;
             for (;;) {
-                const double reward = env_step<MODE, PRECISE>(sm, kp, g, v_out);
+                // multiagent.py:30,35-36: _step(add_wind=False) leaves the action alone; the burn-in steps of a reset
+                // always go through step() with the default add_wind=True (multiagent.py:59-61)
+                const double reward = env_step<MODE, PRECISE>(sm, kp, g, v_out, (r < 0 && !kp.wind_step) ? 0.0 : kp.wind,
+                                                              (r < 0 && it == 0) ? (long long)blockIdx.x : -1);
                 if (r < 0) {
                     // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
                     elapsed = sm.st.misc[0] + 1;
@@ -153,6 +174,7 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             if (g.tid == 0) {
                 st.elapsed[e] = elapsed;
                 if (dyn) sm.mail[1] = grabbed;          // read by everybody after the next iteration's barrier
+                if (it == 0) trace_mark(kp, blockIdx.x, TR_STEPPED);
             }
 
             if (raster && it >= 1) bar_sync<BAR_EMPTY>(n_all);   // the raster group has read the previous env's points
@@ -178,6 +200,12 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             if (kp.publish) {   // tell the concurrently running k_raster_follow that env e's new state is in memory
                 g.sync();
                 if (g.tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(work + 2 + e), "r"(1u) : "memory");
+            }
+            if (it == 0 && g.tid == 0) trace_mark(kp, blockIdx.x, TR_STORED);
+            if (self_raster) {  // state_processors.py:29-42 of the state just written, straight from the stage buffer
+                g.sync();       // [xs | as] of the stage buffer are contiguous = vstack([x, xa])
+                env_raster(sm, sm.st.xs, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma,
+                           NoRelease(), it == 0 ? (long long)blockIdx.x : -1);
             }
             e = e1;
             if (!dyn) e1 = e + gridDim.x;
@@ -222,7 +250,8 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             if (e < 0) break;
             if (!early) zero_fill(e);
             auto release = [n_all]() { bar_arrive<BAR_EMPTY>(n_all); };   // the force group always waits for it
-            env_raster(sm, sm.rx, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma, release);
+            env_raster(sm, sm.rx, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma, release,
+                       it == 0 ? (long long)blockIdx.x : -1);
         }
     }
 }
@@ -234,11 +263,11 @@ __global__ void __maxnreg__(64) k_reset(const KP kp, const SwarmState st, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, 0);
     const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const uint32_t ep = st.episode[e];
     const ResetCtx rc = reset_begin(sm, kp, g, e, ep, has_draws != 0, dr);
-    for (int r = 0; !reset_row(sm, kp, g, rc, r, dr, st); ++r) env_step<MODE, PRECISE>(sm, kp, g, nullptr);
+    for (int r = 0; !reset_row(sm, kp, g, rc, r, dr, st); ++r) env_step<MODE, PRECISE>(sm, kp, g, nullptr, kp.wind);
     double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * kp.N;
     double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * kp.A;
     for (int i = g.tid; i < kp.N; i += g.n) ox[i] = sm.st.xs[i];
@@ -254,12 +283,14 @@ __global__ void __maxnreg__(64) k_reset(const KP kp, const SwarmState st, const 
 // waits for k_step to publish the env (ready[e], release/acquire), reads the fresh positions from L2, rasterises
 // and clears the flag again.  k_step then runs in its fastest shape (one hardware-scheduled CTA per env) and the
 // rasteriser's latency chains cost it no shared memory, registers or barriers.
+constexpr unsigned long long kFollowTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
 __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double* __restrict__ x,
                                                        const double* __restrict__ xa, float* __restrict__ grid,
                                                        uint8_t* __restrict__ positions, uint32_t* ready) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = kp.N, A = kp.A, cells = kp.G * kp.G;
-    const Smem sm = carve(smem_raw, N, A, kp.G, 0, false, 0);
+    const Smem sm = carve(smem_raw, N, A, kp.G, 0, false, 0, 1, 1);
     const RGrp g = {(int)threadIdx.x, (int)blockDim.x};
     const bool tma = tma_zero_fill_ok(grid, cells);
     const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
@@ -274,11 +305,21 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
             raster_zero_fill(grid_e, cells, g.tid, g.n);
         }
         if (g.tid == 0) {
+            // Bounded spin: the step kernel normally publishes within microseconds.  If it never does (it faulted, or a
+            // tool serialised the two kernels follower-first) this kernel traps after kFollowTimeoutNs instead of hanging
+            // the device: the caller sees a CUDA error (SWARM_ERR_LAUNCH) at its next synchronisation.
             uint32_t v;
-            for (;;) {
+            unsigned long long t0 = 0;
+            for (unsigned spins = 0;; ++spins) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready + e) : "memory");
                 if (v) break;
                 __nanosleep(200);
+                if ((spins & 1023u) == 1023u) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > kFollowTimeoutNs) __trap();
+                }
             }
         }
         g.sync();
@@ -287,7 +328,7 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
         for (int i = g.tid; i < N; i += g.n) pts[i] = __ldcg(gx + i);
         for (int k = g.tid; k < A; k += g.n) pts[N + k] = __ldcg(ga + k);
         g.sync();
-        env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, NoRelease());
+        env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, NoRelease(), (long long)kp.E + e);
         if (g.tid == 0) ready[e] = 0u;          // consumed: the next step's k_step raises it again
     }
 }
@@ -299,7 +340,7 @@ __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     const int cells = kp.G * kp.G;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 0, false, 0);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 0, false, 0, 1, 1);
     const RGrp g = {(int)threadIdx.x, (int)blockDim.x};
     float* grid_e = grid + (size_t)e * cells * 2;
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
@@ -328,7 +369,7 @@ __global__ void __maxnreg__(64) k_forces(const KP kp, const double* __restrict__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     constexpr int T = ModeT<MODE>::T;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, 0);
     const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
@@ -338,17 +379,17 @@ __global__ void __maxnreg__(64) k_forces(const KP kp, const double* __restrict__
     stage_locusts<MODE>(sm, kp, g);
     g.sync();
     float vx[T], vy[T];
-    const double en = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
-    energy_put(sm, g, en);
+    pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
+    energy_put<MODE>(sm, kp, g, vx, vy);
     if (v) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const int j = target_index<MODE>(g, t);
+            const int j = target_index<MODE>(g, t, kp);
             if (j < kp.N) reinterpret_cast<float2*>(v)[(size_t)e * kp.N + j] = make_float2(vx[t], vy[t]);
         }
     }
     g.sync();
-    const double r = energy_get(sm, kp, g);
+    const double r = energy_get<MODE>(sm, kp, g);
     if (reward && g.tid == 0) reward[e] = (float)r;
 }
 
@@ -429,6 +470,10 @@ __global__ void k_philox_raw(const uint4* __restrict__ ctr, const uint2* __restr
 
 thread_local char g_cuda_err[256] = "";
 
+// debug timeline buffer (swarm_debug_trace); process-wide, nullptr in production
+unsigned long long* g_trace = nullptr;
+long long g_trace_slots = 0;
+
 int cuda_fail(cudaError_t err, const char* what) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(err));
     return SWARM_ERR_LAUNCH;
@@ -436,20 +481,23 @@ int cuda_fail(cudaError_t err, const char* what) {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kMaxLocusts = 2048;
+constexpr int kMaxThreads = 1024;
 
-// N <= 512: unordered pairs -- MODE 3 (64-wide super-tiles, two targets per lane) when N pads to a
-// multiple of 64 anyway, else MODE 1 (32-wide tiles, one target per lane); N > 512: ordered pairs
-// with 2 or 4 targets per thread (MODE 2/4).
-int force_mode(int N) {
-    if (N <= kSymMaxLocusts) return ((N + 63) / 64) * 64 == ((N + 31) / 32) * 32 ? 3 : 1;
+// N <= 512: unordered pairs -- the MODE 3 family (64-wide super-tiles, two targets per lane; ks = 1, 2 or 4 warps per
+// super-tile -> MODE 3, 5, 6) when N pads to a multiple of 64 anyway, else MODE 1 (32-wide tiles, one target per
+// lane); N > 512: ordered pairs with 2 or 4 targets per thread (MODE 2/4).
+bool sym64_ok(int N) { return N <= kSymMaxLocusts && ((N + 63) / 64) * 64 == ((N + 31) / 32) * 32; }
+int force_mode(int N, int ks = 1) {
+    if (sym64_ok(N)) return ks >= 4 ? 6 : (ks == 2 ? 5 : 3);
+    if (N <= kSymMaxLocusts) return 1;
     return N <= 1024 ? 2 : 4;
 }
-int force_sym(int mode) { return mode == 1 ? 1 : (mode == 3 ? 2 : 0); }
+int force_sym(int mode) { return mode == 1 ? 1 : ((mode == 3 || mode == 5 || mode == 6) ? 2 : 0); }
+int mode_ks(int mode) { return mode == 5 ? 2 : (mode == 6 ? 4 : 1); }
 
 // threads of the force group
-int block_threads(int N) {
-    const int mode = force_mode(N);
-    if (mode == 3) return ((N + 63) / 64) * 32;
+int block_threads(int N, int mode) {
+    if (force_sym(mode) == 2) return mode_ks(mode) * ((N + 63) / 64) * 32;
     const int per = (N + mode - 1) / mode;
     return ((per + 31) / 32) * 32;
 }
@@ -458,8 +506,9 @@ int block_threads(int N) {
 // measured: 64 raster threads beat 32 for small swarms (1024 x 64: 14.2 vs 17.6 us per step)
 int raster_threads(int N, int A) { return (N + A) <= 1024 ? 64 : 128; }
 
-size_t step_smem(const SwarmParams* p, bool raster, int n_stage = 2) {
-    return smem_bytes(p->n_locusts, p->n_agents, p->grid_size, n_stage, true, raster, force_sym(force_mode(p->n_locusts)));
+// raster: 0 none, 1 raster group (own point buffer), 2 the force group rasterises
+size_t step_smem(const SwarmParams* p, int raster, int n_stage, int mode) {
+    return smem_bytes(p->n_locusts, p->n_agents, p->grid_size, n_stage, true, raster, force_sym(mode), mode_ks(mode));
 }
 
 int validate(const SwarmParams* p, int min_agents = 1) {
@@ -469,13 +518,16 @@ int validate(const SwarmParams* p, int min_agents = 1) {
     if (p->grid_size < 2 || p->grid_size > 255) return SWARM_ERR_SIZE;      // positions are uint8
     if (p->n_burn_in < 0 || p->max_episode_steps < 0) return SWARM_ERR_SIZE;
     if (p->math_mode != 0 && p->math_mode != 1) return SWARM_ERR_FLAGS;
-    if (step_smem(p, true) > kMaxSmem) return SWARM_ERR_SIZE;
+    if (p->tuning < 0 || p->tuning > 0x3f) return SWARM_ERR_FLAGS;
+    if (step_smem(p, 1, 2, force_mode(p->n_locusts)) > kMaxSmem) return SWARM_ERR_SIZE;
     if (p->env_id_offset < 0 || p->env_id_offset + p->n_envs > (int64_t)0xffffffffLL) return SWARM_ERR_SIZE;
     return SWARM_OK;
 }
 
-KP make_kp(const SwarmParams* p) {
+KP make_kp(const SwarmParams* p, int mode = 0) {
     KP k;
+    memset(&k, 0, sizeof(k));
+    if (!mode) mode = force_mode(p->n_locusts);
     k.E = p->n_envs; k.N = p->n_locusts; k.A = p->n_agents; k.G = p->grid_size;
     k.n_burn = p->n_burn_in; k.max_steps = p->max_episode_steps;
     k.sigma = p->noise; k.wind = p->wind; k.dt = p->dt;
@@ -490,13 +542,27 @@ KP make_kp(const SwarmParams* p) {
     k.dynamic = 0;
     k.publish = 0;
     k.n_stage = 2;
+    k.ks = mode_ks(mode);
+    k.raster = 0;
+    k.wind_step = 1;
+    if (force_sym(mode) == 2) sym64_chunks(k.N, k.cb);
+    // numpy: linspace(0, 2 HEIGHT, G + 1) has step (hi - lo) / G, rounded once (state_processors.py:31-32)
+    k.step_y = (k.y_hi - 0.0) / (double)k.G;
+    k.inv_y = 1.0 / k.step_y;
+    k.inv_x = (double)k.G / (2.0 * k.half_w);
+    k.inv_P = 1.0 / (double)(k.N + k.A);
+    k.inv_G = 1.0 / (double)k.G;
+    k.trace = g_trace;
+    k.trace_slots = g_trace_slots;
     return k;
 }
 
 // Per (device, kernel) launch cache: the opt-in shared-memory ceiling already granted and the
 // occupancy (CTAs/SM) of the configurations seen, so that the steady-state cost of an entry
 // point is one cudaGetDevice + one launch.
-// side stream (higher priority) + fork/join events of the two-kernel step, one set per device
+// Side stream (higher priority) + fork/join events of the two-kernel step: one set per (device, caller stream), so
+// that calls on different streams -- from one host thread or several -- never share an event or serialise their
+// followers, and a stream that is being captured only ever pulls ITS side stream into the capture.
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -504,9 +570,10 @@ struct SideStream {
 
 struct KernelCache {
     std::mutex mu;
-    std::map<int, SideStream> side;
+    std::map<std::pair<int, cudaStream_t>, SideStream> side;
     std::map<std::pair<int, const void*>, size_t> smem_set;
     std::map<std::tuple<int, const void*, int, size_t>, int> occupancy;
+    std::map<std::pair<int, const void*>, int> regs;
     std::map<int, int> sms;
 };
 KernelCache& cache() {
@@ -543,9 +610,9 @@ int prep(K kernel, size_t smem) {
     return SWARM_OK;
 }
 
-// grid of a persistent kernel: every SM filled to its occupancy, never more CTAs than envs
+// occupancy (CTAs per SM) of a launch shape and the SM count of the current device
 template <typename K>
-int persistent_grid(K kernel, int threads, size_t smem, int n_envs, int* grid, int* n_sms = nullptr) {
+int occupancy(K kernel, int threads, size_t smem, int* per_sm_out, int* n_sms = nullptr) {
     int dev = 0;
     if (int rc = current_device(&dev)) return rc;
     KernelCache& c = cache();
@@ -565,34 +632,34 @@ int persistent_grid(K kernel, int threads, size_t smem, int n_envs, int* grid, i
         cudaError_t err = cudaFuncGetAttributes(&fa, kernel);        // also forces the (lazily loaded) kernel in
         if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
         if (err != cudaSuccess) return cuda_fail(err, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-        if (per_sm < 1) per_sm = 1;
+        c.regs[std::make_pair(dev, (const void*)kernel)] = fa.numRegs;
         o = c.occupancy.emplace(key, per_sm).first;
     }
-    const long long slots = (long long)s->second * o->second;
-    *grid = (int)(n_envs < slots ? n_envs : slots);
+    *per_sm_out = o->second;
     if (n_sms) *n_sms = s->second;
     return SWARM_OK;
 }
 
-int side_stream(SideStream* out) {
+// grid of a persistent kernel: every SM filled to its occupancy, never more CTAs than envs
+template <typename K>
+int persistent_grid(K kernel, int threads, size_t smem, int n_envs, int* grid, int* n_sms = nullptr) {
+    int per_sm = 0, sms = 1;
+    if (int rc = occupancy(kernel, threads, smem, &per_sm, &sms)) return rc;
+    if (per_sm < 1) per_sm = 1;
+    const long long slots = (long long)sms * per_sm;
+    *grid = (int)(n_envs < slots ? n_envs : slots);
+    if (n_sms) *n_sms = sms;
+    return SWARM_OK;
+}
+
+// registers per thread of a kernel occupancy() has seen on the current device (0 if unknown)
+int kernel_regs(const void* kernel) {
     int dev = 0;
-    if (int rc = current_device(&dev)) return rc;
+    if (current_device(&dev)) return 0;
     KernelCache& c = cache();
     std::lock_guard<std::mutex> lk(c.mu);
-    SideStream& ss = c.side[dev];
-    if (!ss.stream) {
-        int lo = 0, hi = 0;
-        cudaError_t err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, hi);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
-        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming);
-        if (err != cudaSuccess) {
-            ss = SideStream();
-            return cuda_fail(err, "side stream");
-        }
-    }
-    *out = ss;
-    return SWARM_OK;
+    auto r = c.regs.find(std::make_pair(dev, kernel));
+    return r == c.regs.end() ? 0 : r->second;
 }
 
 int check_launch(const char* what) {
@@ -605,21 +672,41 @@ int check_launch(const char* what) {
         case 1: { constexpr int TT = 1; __VA_ARGS__; } break; \
         case 2: { constexpr int TT = 2; __VA_ARGS__; } break; \
         case 3: { constexpr int TT = 3; __VA_ARGS__; } break; \
+        case 5: { constexpr int TT = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int TT = 6; __VA_ARGS__; } break; \
         default: { constexpr int TT = 4; __VA_ARGS__; } break; \
     }
 
-// swarm_step_host keeps the launches of its last argument set as an instantiated graph
+// swarm_step_host keeps the launches of its last argument sets as instantiated graphs (per host thread)
 struct HostStepKey {
     SwarmParams p;
     SwarmState st;
     SwarmStepIO io;
+    float* host_grid;
+    uint8_t* host_positions;
     int device;
 };
-struct HostStepGraph {
-    HostStepKey key;
-    cudaGraphExec_t exec = nullptr;
-};
 constexpr int kHostGraphs = 32;     // distinct (params, state, buffers) argument sets kept per host thread
+struct HostStepCache {
+    struct Entry {
+        HostStepKey key;
+        cudaGraphExec_t exec = nullptr;
+    } entries[kHostGraphs];
+    unsigned next_victim = 0;
+    bool capture_failure_reported = false;
+    void clear() {
+        for (Entry& e : entries)
+            if (e.exec) {
+                cudaGraphExecDestroy(e.exec);
+                e.exec = nullptr;
+            }
+    }
+    ~HostStepCache() { clear(); }       // thread exit: the graphs go with the thread
+};
+HostStepCache& host_cache() {
+    static thread_local HostStepCache c;
+    return c;
+}
 
 // device-visible alias of a pinned (page-locked, UVA-mapped) host pointer, or nullptr
 template <typename T>
@@ -639,6 +726,8 @@ StepKernel step_kernel(int mode, bool precise) {
         case 1: return precise ? k_step<1, true> : k_step<1, false>;
         case 2: return precise ? k_step<2, true> : k_step<2, false>;
         case 3: return precise ? k_step<3, true> : k_step<3, false>;
+        case 5: return precise ? k_step<5, true> : k_step<5, false>;
+        case 6: return precise ? k_step<6, true> : k_step<6, false>;
         default: return precise ? k_step<4, true> : k_step<4, false>;
     }
 }
@@ -647,6 +736,39 @@ const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr
 
 bool draws_complete(const SwarmInjectedDraws* d) {
     return d->x0 && d->xa0 && d->burn_actions && d->agent_noise && d->particle_noise;
+}
+
+// ---- launch shape of swarm_step ------------------------------------------------------------------------------
+// WHERE the observation is produced (same results every way):
+//   FOLLOW  k_raster_follow on the side stream trails a rasteriser-less, one-env-per-CTA k_step (needs 2 + E flags)
+//   WARPS   a raster warp group inside persistent k_step CTAs, one env behind the force group
+//   SELF    the step's own threads rasterise their env right after stepping it (one env per CTA)
+enum RasterPlace { RASTER_NONE = 0, RASTER_FOLLOW = 1, RASTER_WARPS = 2, RASTER_SELF = 3 };
+
+struct StepShape {
+    int mode;        // force mode (1..6)
+    int place;       // RasterPlace
+    int follow_threads, follow_per_sm;
+    size_t follow_smem;
+};
+
+bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+// Warps per 64-locust super-tile: batches that cannot fill the SMs with one warp per super-tile get 2 or 4, so that the
+// XU pipe still sees ~6+ warps per scheduler (measured on B200: 512 x 256 has 3.5 warps per scheduler at ks = 1 and
+// runs the pair loop at 55 % of the XU rate a full machine reaches).
+int pick_ks(const SwarmParams* p, int sms) {
+    if (!sym64_ok(p->n_locusts)) return 1;
+    const int nt2 = (p->n_locusts + 63) / 64;
+    const long long warps = (long long)p->n_envs * nt2;
+    const long long want = (long long)sms * 4 * 6;
+    int ks = 1;
+    while (ks < 4 && warps * ks < want) ks *= 2;
+    while (ks > 1 && ks * nt2 * 32 > kMaxThreads) ks /= 2;
+    return ks;
 }
 
 }  // namespace
@@ -678,11 +800,21 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
     if (rc) return rc;
     if (!st || !st->x || !st->xa || !st->noise_x || !st->noise_a || !st->elapsed || !st->episode) return SWARM_ERR_NULL;
     if (draws && !draws_complete(draws)) return SWARM_ERR_NULL;
-    const KP kp = make_kp(p);
-    const size_t smem = step_smem(p, false, 1);
-    const int nt = block_threads(kp.N);
+    int sms = 148;
+    {
+        int dev = 0;
+        if ((rc = current_device(&dev))) return rc;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
+    if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
+    const int mode = force_mode(p->n_locusts, ks);
+    const KP kp = make_kp(p, mode);
+    const size_t smem = step_smem(p, 0, 1, mode);
+    const int nt = block_threads(kp.N, mode);
+    if (nt > kMaxThreads) return SWARM_ERR_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(force_mode(kp.N),
+    DISPATCH_T(mode,
         if (p->math_mode) {
             if ((rc = prep(k_reset<TT, true>, smem))) return rc;
             k_reset<TT, true><<<kp.E, nt, smem, s>>>(kp, *st, mask, draws ? *draws : kNoDraws, draws ? 1 : 0);
@@ -702,40 +834,96 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     if (!io->reward || !io->done) return SWARM_ERR_NULL;
     if ((io->flags & SWARM_STEP_ACTIONS_F64) ? !io->actions_f64 : !io->actions_f32) return SWARM_ERR_NULL;
     if ((io->grid != nullptr) != (io->positions != nullptr)) return SWARM_ERR_FLAGS;
-    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64)) return SWARM_ERR_FLAGS;
+    if (io->flags & ~(SWARM_STEP_AUTO_RESET | SWARM_STEP_CLIP_ACTIONS | SWARM_STEP_ACTIONS_F64 | SWARM_STEP_NO_ACTION_WIND |
+                      SWARM_STEP_INKERNEL_RASTER))
+        return SWARM_ERR_FLAGS;
     if (reset_draws && !draws_complete(reset_draws)) return SWARM_ERR_NULL;
-    KP kp = make_kp(p);
+    if (st->work_words && !st->work) return SWARM_ERR_NULL;
+    const int N = p->n_locusts, A = p->n_agents, E = p->n_envs;
     const bool want_grid = io->grid != nullptr;
-    // With the scratch words (SwarmState::work, 2 + E of them) the observation is produced by a second kernel that
-    // follows the step on a higher-priority stream (k_raster_follow); without, by the raster warps of k_step itself.
-    // The follower spins until the step publishes an env, so the step must always be able to get onto an SM next to it.
-    const int follow_threads = (kp.N + kp.A) <= 128 ? 32 : 128;
-    const size_t follow_smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, true, 0);
+    const bool have_queue = st->work != nullptr && st->work_words >= 2;
+    const bool have_flags = st->work != nullptr && st->work_words >= 2 + (uint64_t)E;
+    int sms = 148;
+    {
+        int dev = 0;
+        if ((rc = current_device(&dev))) return rc;
+        KernelCache& c = cache();
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.sms.find(dev);
+        if (it == c.sms.end()) {
+            int n = 0;
+            cudaError_t err = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceGetAttribute");
+            it = c.sms.emplace(dev, n).first;
+        }
+        sms = it->second;
+    }
+    // ---- launch shape (automatic, or forced through SwarmParams::tuning)
+    const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
+    if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
+    const int mode = force_mode(N, ks);
+    const int nf = block_threads(N, mode);
+    if (nf > kMaxThreads) return SWARM_ERR_SIZE;
+    // With the per-env flags the observation can be produced by a second kernel that follows the step on a higher-priority
+    // stream (k_raster_follow).  The follower spins until the step publishes an env, so the step must always be able to get
+    // onto an SM next to it: shared memory, threads AND registers of both have to fit (checked below).
+    const int follow_threads = (N + A) <= 128 ? 32 : 128;
+    const size_t follow_smem = smem_bytes(N, A, p->grid_size, 0, false, 1, 0, 1);
     // raster CTAs per SM that keep pace with the step (measured at 4096 envs: N = 160: 4 -> 0.110 ms, 2 -> 0.118; N = 192 and up: 2)
-    int follow_per_sm = (kp.N + kp.A) <= 128 ? 6 : (kp.N < 192 ? 4 : 2);
-    while (follow_per_sm > 0 && follow_per_sm * (follow_smem + 1024) + step_smem(p, false, 1) + 1024 > kMaxSmem) --follow_per_sm;
-    // Measured (B200, 4096 envs): the follower wins for large swarms (N = 256: 0.181 vs 0.199 ms, N = 192: 0.123 vs
-    // 0.135), the in-kernel raster warps for small ones, where the rasteriser -- not the forces -- is the critical path
-    // (N = 128: 0.080 vs 0.108 ms, N = 64: 0.052 vs 0.069); N = 160 is the break-even.
-    const bool follow = want_grid && st->work != nullptr && kp.N >= 160 && follow_per_sm > 0 &&
-                        follow_per_sm * follow_threads + block_threads(kp.N) <= 2048;
-    const bool raster = want_grid && !follow;
-    kp.n_stage = raster ? 2 : 1;          // one env per CTA (no raster warps): nothing to prefetch into a second buffer
-    const size_t smem = step_smem(p, raster, kp.n_stage);
-    const int nf = block_threads(kp.N);
-    const int nt = nf + (raster ? raster_threads(kp.N, kp.A) : 0);
+    int follow_per_sm = (N + A) <= 128 ? 6 : (N < 192 ? 4 : 2);
+    while (follow_per_sm > 0 &&
+           follow_per_sm * (follow_smem + 1024) + step_smem(p, 0, 1, mode) + 1024 > kMaxSmem) --follow_per_sm;
+    const bool no_follower = (io->flags & SWARM_STEP_INKERNEL_RASTER) || env_flag("SWARM_B200_NO_FOLLOWER");
+    const StepKernel kernel = step_kernel(mode, p->math_mode != 0);
+    bool follow_fits = have_flags && !no_follower && follow_per_sm > 0 && follow_per_sm * follow_threads + nf <= 2048;
+    int rgrid = 0;
+    if (want_grid && follow_fits) {
+        // registers: follow_per_sm follower CTAs must leave room for at least one step CTA on every SM
+        const size_t smem0 = step_smem(p, 0, 1, mode);
+        int o = 0;
+        if ((rc = prep(kernel, smem0)) || (rc = occupancy(kernel, nf, smem0, &o))) return rc;
+        if ((rc = prep(k_raster_follow, follow_smem))) return rc;
+        if ((rc = persistent_grid(k_raster_follow, follow_threads, follow_smem, E, &rgrid))) return rc;
+        const long long rs = kernel_regs((const void*)kernel), rf = kernel_regs((const void*)k_raster_follow);
+        while (follow_per_sm > 1 && follow_per_sm * follow_threads * rf + nf * rs > 65536) --follow_per_sm;
+        if (follow_per_sm * follow_threads * rf + nf * rs > 65536) follow_fits = false;
+        if (rgrid > sms * follow_per_sm) rgrid = sms * follow_per_sm;
+    }
+    const bool warps_fit = nf + raster_threads(N, A) <= kMaxThreads && step_smem(p, 1, 2, mode) <= kMaxSmem;
+    int place = RASTER_NONE;
+    if (want_grid) {
+        const int forced = (p->tuning >> 4) & 3;
+        // Measured (B200, 4096 envs): the follower wins for large swarms in multi-wave batches (N = 256: 0.181 vs 0.199 ms,
+        // N = 192: 0.123 vs 0.135), the raster warps for small swarms, where the rasteriser -- not the forces -- is the
+        // critical path (N = 128: 0.080 vs 0.108 ms, N = 64: 0.052 vs 0.069).  Batches of at most about one wave of
+        // one-env CTAs have nothing to hide the rasteriser under: there the step's own threads rasterise (SELF).
+        const int per_sm = 65536 / (64 * nf) > 0 ? 65536 / (64 * nf) : 1;
+        if (forced) place = forced;
+        else if (E <= (long long)sms * per_sm) place = RASTER_SELF;
+        else if (N >= 160) place = RASTER_FOLLOW;
+        else place = RASTER_WARPS;
+        if (place == RASTER_FOLLOW && !follow_fits) place = RASTER_WARPS;
+        if (place == RASTER_WARPS && !warps_fit) place = RASTER_SELF;
+    }
+    const bool follow = place == RASTER_FOLLOW, warps = place == RASTER_WARPS, self = place == RASTER_SELF;
+    KP kp = make_kp(p, mode);
+    kp.raster = warps ? 1 : (self ? 2 : 0);
+    kp.n_stage = warps ? 2 : 1;           // one env per CTA (no raster warps): nothing to prefetch into a second buffer
+    kp.wind_step = (io->flags & SWARM_STEP_NO_ACTION_WIND) ? 0 : 1;
+    const size_t smem = step_smem(p, kp.raster, kp.n_stage, mode);
+    if (smem > kMaxSmem) return SWARM_ERR_SIZE;
+    const int nt = nf + (warps ? raster_threads(N, A) : 0);
     const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;
     const int has = reset_draws ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const StepKernel kernel = step_kernel(force_mode(kp.N), p->math_mode != 0);
     if ((rc = prep(kernel, smem))) return rc;
-    int grid = 0, sms = 1;
-    if ((rc = persistent_grid(kernel, nt, smem, kp.E, &grid, &sms))) return rc;
+    int grid = 0;
+    if ((rc = persistent_grid(kernel, nt, smem, E, &grid))) return rc;
     // without raster warps to overlap there is nothing to gain from persistence, and hardware-scheduled one-env
     // CTAs measure 8 % faster (C4: 0.154 vs 0.166 ms)
-    if (!raster) grid = kp.E;
+    if (!warps) grid = E;
     // the work queue pays off when every CTA has several large envs to work through (one contended atomic per env)
-    kp.dynamic = (raster && st->work && kp.E >= 3 * grid && (long long)kp.N * (kp.N + kp.A) >= 16384) ? 1 : 0;
+    kp.dynamic = (warps && have_queue && E >= 3 * grid && (long long)N * (N + A) >= 16384) ? 1 : 0;
     if (!follow) {
         kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
         return check_launch("swarm_step");
@@ -744,16 +932,32 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     // device that cannot co-schedule them) the step simply finishes before the follower starts and finds every
     // flag raised -- slower, never dead-locked.  Run concurrently, the follower's CTAs (higher-priority stream)
     // take the first SM slots the step's one-env CTAs free up and then trail it by one env.
-    SideStream ss;
-    if ((rc = side_stream(&ss))) return rc;
-    if ((rc = prep(k_raster_follow, follow_smem))) return rc;
-    int rgrid = 0;
-    if ((rc = persistent_grid(k_raster_follow, follow_threads, follow_smem, kp.E, &rgrid))) return rc;
-    if (rgrid > sms * follow_per_sm) rgrid = sms * follow_per_sm;
-    cudaError_t err = cudaEventRecord(ss.fork, s);
+    kp.publish = 1;
+    int dev = 0;
+    if ((rc = current_device(&dev))) return rc;
+    KernelCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);          // fork, both launches and join of one call are never interleaved with another's
+    SideStream& ss = c.side[std::make_pair(dev, s)];
+    cudaError_t err = cudaSuccess;
+    if (!ss.stream) {
+        // first call on this stream; it may be inside a stream capture (the caller warmed up on another stream):
+        // creating a stream / events is harmless there, so step out of the capture's API restrictions for it
+        cudaStreamCaptureMode cm = cudaStreamCaptureModeRelaxed;
+        cudaThreadExchangeStreamCaptureMode(&cm);
+        int lo = 0, hi = 0;
+        err = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&ss.stream, cudaStreamNonBlocking, hi);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming);
+        cudaThreadExchangeStreamCaptureMode(&cm);
+        if (err != cudaSuccess) {
+            ss = SideStream();
+            return cuda_fail(err, "side stream");
+        }
+    }
+    err = cudaEventRecord(ss.fork, s);
     if (err == cudaSuccess) err = cudaStreamWaitEvent(ss.stream, ss.fork, 0);
     if (err != cudaSuccess) return cuda_fail(err, "fork");
-    kp.publish = 1;
     kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
     if ((rc = check_launch("swarm_step"))) return rc;
     k_raster_follow<<<rgrid, follow_threads, follow_smem, ss.stream>>>(kp, st->x, st->xa, io->grid, io->positions,
@@ -765,57 +969,81 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     return check_launch("swarm_step");
 }
 
+void swarm_step_host_clear(void) { host_cache().clear(); }
+
+void swarm_debug_trace(uint64_t* device_words, int64_t n_words) {
+    g_trace = reinterpret_cast<unsigned long long*>(device_words);
+    g_trace_slots = device_words ? n_words / 16 : 0;
+}
+
 int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const float* host_actions,
-                    float* host_reward, uint8_t* host_done, swarm_stream_t stream) {
-    if (!p || !io || !host_actions || !host_reward || !host_done) return SWARM_ERR_NULL;
+                    float* host_reward, uint8_t* host_done, float* host_grid, uint8_t* host_positions,
+                    swarm_stream_t stream) {
+    if (!p || !st || !io || !host_actions || !host_reward || !host_done) return SWARM_ERR_NULL;
     if ((io->flags & SWARM_STEP_ACTIONS_F64) || !io->actions_f32) return SWARM_ERR_FLAGS;
+    if ((host_grid != nullptr) != (host_positions != nullptr)) return SWARM_ERR_FLAGS;
+    if (host_grid && !io->grid) return SWARM_ERR_FLAGS;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t err;
+    const size_t grid_bytes = (size_t)p->n_envs * p->grid_size * p->grid_size * 2 * sizeof(float);
+    const size_t pos_bytes = (size_t)p->n_envs * p->n_agents * 2;
+    // the observation goes back through the copy engine after the step (D2H over PCIe, ordered on the stream)
+    auto obs_back = [&](cudaStream_t on) -> int {
+        if (!host_grid) return SWARM_OK;
+        cudaError_t e = cudaMemcpyAsync(host_grid, io->grid, grid_bytes, cudaMemcpyDeviceToHost, on);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host_positions, io->positions, pos_bytes, cudaMemcpyDeviceToHost, on);
+        return e == cudaSuccess ? SWARM_OK : cuda_fail(e, "D2H observation");
+    };
     // Zero-copy path: with pinned host buffers the kernel itself pulls each env's 80 bytes of actions over
     // PCIe (its cp.async prefetch runs one env ahead, so the latency hides under the previous env's force
     // phase) and posts reward/done straight into host memory: no staging copies, one launch, one sync.
     float* d_act = mapped_host(const_cast<float*>(host_actions));
     float* d_rew = mapped_host(host_reward);
     uint8_t* d_done = mapped_host(host_done);
-    if (d_act && d_rew && d_done) {
+    const bool obs_pinned = !host_grid || (mapped_host(host_grid) && mapped_host(host_positions));
+    if (d_act && d_rew && d_done && obs_pinned) {
         SwarmStepIO direct = *io;
         direct.actions_f32 = d_act;
         direct.reward = d_rew;
         direct.done = d_done;
         // The same call repeats every step with the same buffers: keep its launches (step kernel, and for large
-        // swarms fork -> follower -> join on the side stream) as ONE instantiated CUDA graph per argument set.
-        // UseNodePriority matters: the follower only runs NEXT TO the step if its kernel node keeps the side
-        // stream's higher priority (with equal priorities the step's CTAs are all dispatched first: 0.255 vs 0.189 ms).
-        static thread_local HostStepGraph cache_entries[kHostGraphs];
-        static thread_local unsigned next_victim = 0;
+        // swarms fork -> follower -> join on the side stream, then the observation copies) as ONE instantiated CUDA
+        // graph per argument set.  UseNodePriority matters: the follower only runs NEXT TO the step if its kernel node
+        // keeps the side stream's higher priority (with equal priorities the step's CTAs are all dispatched first:
+        // 0.255 vs 0.189 ms).
+        HostStepCache& hc = host_cache();
         HostStepKey key;
         memset(&key, 0, sizeof(key));
-        key.p = *p; key.st = *st; key.io = direct;
+        key.p = *p; key.st = *st; key.io = direct; key.host_grid = host_grid; key.host_positions = host_positions;
         if (cudaGetDevice(&key.device) != cudaSuccess) key.device = -1;
         cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(s, &capturing);
         if (capturing == cudaStreamCaptureStatusNone && key.device >= 0) {
-            HostStepGraph* hit = nullptr;
+            HostStepCache::Entry* hit = nullptr;
             for (int i = 0; i < kHostGraphs; ++i)
-                if (cache_entries[i].exec && memcmp(&cache_entries[i].key, &key, sizeof(key)) == 0) hit = &cache_entries[i];
+                if (hc.entries[i].exec && memcmp(&hc.entries[i].key, &key, sizeof(key)) == 0) hit = &hc.entries[i];
             if (!hit) {
-                HostStepGraph& cached = cache_entries[next_victim++ % kHostGraphs];      // round-robin replacement
+                HostStepCache::Entry& cached = hc.entries[hc.next_victim++ % kHostGraphs];      // round-robin replacement
                 if (cached.exec) { cudaGraphExecDestroy(cached.exec); cached.exec = nullptr; }
                 // one plain call first: it warms the per-kernel caches (attribute / occupancy queries are not
                 // capturable) and is itself this step
-                const int rc = swarm_step(p, st, &direct, nullptr, stream);
+                int rc = swarm_step(p, st, &direct, nullptr, stream);
+                if (rc == SWARM_OK) rc = obs_back(s);
                 if (rc) return rc;
                 err = cudaStreamSynchronize(s);
                 if (err != cudaSuccess) return cuda_fail(err, "stream sync");
                 cudaStream_t cap = nullptr;
                 cudaGraph_t graph = nullptr;
+                bool ok = false;
                 if (cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) == cudaSuccess) {
                     if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                        const int rc2 = swarm_step(p, st, &direct, nullptr, (swarm_stream_t)cap);
+                        int rc2 = swarm_step(p, st, &direct, nullptr, (swarm_stream_t)cap);
+                        if (rc2 == SWARM_OK) rc2 = obs_back(cap);
                         const cudaError_t e2 = cudaStreamEndCapture(cap, &graph);
                         if (rc2 == SWARM_OK && e2 == cudaSuccess && graph &&
                             cudaGraphInstantiateWithFlags(&cached.exec, graph, cudaGraphInstantiateFlagUseNodePriority) == cudaSuccess) {
                             cached.key = key;
+                            ok = true;
                         } else {
                             cached.exec = nullptr;
                         }
@@ -824,6 +1052,11 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
                     cudaStreamDestroy(cap);
                 }
                 cudaGetLastError();       // a failed capture must not poison later calls: the plain path still works
+                if (!ok && !hc.capture_failure_reported) {
+                    hc.capture_failure_reported = true;
+                    fprintf(stderr, "libswarm_b200: swarm_step_host could not capture its launches into a CUDA graph; "
+                                    "falling back to plain launches (slower, same results)\n");
+                }
                 return SWARM_OK;
             }
             err = cudaGraphLaunch(hit->exec, s);
@@ -832,7 +1065,8 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
             if (err != cudaSuccess) return cuda_fail(err, "stream sync");
             return SWARM_OK;
         }
-        const int rc = swarm_step(p, st, &direct, nullptr, stream);
+        int rc = swarm_step(p, st, &direct, nullptr, stream);
+        if (rc == SWARM_OK) rc = obs_back(s);
         if (rc) return rc;
         err = cudaStreamSynchronize(s);
         if (err != cudaSuccess) return cuda_fail(err, "stream sync");
@@ -842,12 +1076,13 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
     const size_t na = (size_t)p->n_envs * p->n_agents * 2 * sizeof(float);
     err = cudaMemcpyAsync(io->actions_f32, host_actions, na, cudaMemcpyHostToDevice, s);
     if (err != cudaSuccess) return cuda_fail(err, "H2D actions");
-    const int rc = swarm_step(p, st, io, nullptr, stream);
+    int rc = swarm_step(p, st, io, nullptr, stream);
     if (rc) return rc;
     err = cudaMemcpyAsync(host_reward, io->reward, (size_t)p->n_envs * sizeof(float), cudaMemcpyDeviceToHost, s);
     if (err != cudaSuccess) return cuda_fail(err, "D2H reward");
     err = cudaMemcpyAsync(host_done, io->done, (size_t)p->n_envs, cudaMemcpyDeviceToHost, s);
     if (err != cudaSuccess) return cuda_fail(err, "D2H done");
+    if ((rc = obs_back(s))) return rc;
     err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) return cuda_fail(err, "stream sync");
     return SWARM_OK;
@@ -860,7 +1095,7 @@ int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa, flo
     if (!x || !grid) return SWARM_ERR_NULL;
     if (p->n_agents > 0 && (!xa || !positions)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, true, 0);
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, 1, 0, 1);
     const int nt = (kp.N + kp.A) <= 128 ? 64 : 128;
     if ((rc = prep(k_rasterize, smem))) return rc;
     k_rasterize<<<kp.E, nt, smem, (cudaStream_t)stream>>>(kp, x, xa, grid, positions, box);
@@ -896,11 +1131,21 @@ int swarm_forces(const SwarmParams* p, const double* x, const double* xa, float*
     int rc = validate(p);
     if (rc) return rc;
     if (!x || !xa || (!v && !reward)) return SWARM_ERR_NULL;
-    const KP kp = make_kp(p);
-    const size_t smem = step_smem(p, false, 1);
-    const int nt = block_threads(kp.N);
+    int sms = 148;
+    {
+        int dev = 0;
+        if ((rc = current_device(&dev))) return rc;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
+    if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
+    const int mode = force_mode(p->n_locusts, ks);
+    const KP kp = make_kp(p, mode);
+    const size_t smem = step_smem(p, 0, 1, mode);
+    const int nt = block_threads(kp.N, mode);
+    if (nt > kMaxThreads) return SWARM_ERR_SIZE;
     cudaStream_t s = (cudaStream_t)stream;
-    DISPATCH_T(force_mode(kp.N),
+    DISPATCH_T(mode,
         if (p->math_mode) {
             if ((rc = prep(k_forces<TT, true>, smem))) return rc;
             k_forces<TT, true><<<kp.E, nt, smem, s>>>(kp, x, xa, v, reward);

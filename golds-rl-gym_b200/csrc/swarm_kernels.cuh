@@ -49,6 +49,17 @@ struct KP {
     int dynamic;      // k_step: draw the third and later envs of a CTA from the work queue (SwarmState::work)
     int n_stage;      // k_step: stage buffers in shared memory (2 = prefetch the CTA's next env, 1 = one env per CTA)
     int publish;      // k_step: raise work[2 + e] once env e's new state is in memory (k_raster_follow waits for it)
+    int ks;           // MODE 3 family: warps that share one 64-locust super-tile (1, 2 or 4; = the kernel's template KS)
+    int raster;       // shared-memory layout of the rasteriser: 0 none, 1 a raster GROUP with its own point buffer, 2 the force
+                      // group rasterises its own env after the step (points = the stage buffer)
+    int wind_step;    // 0: the step proper does not add the wind to the actions (SwarmEnv._step(add_wind=False))
+    unsigned long long* trace;   // debug (swarm_debug_trace): per-CTA phase timestamps, nullptr in production
+    long long trace_slots;       // capacity of trace in 16-word records
+    unsigned char cb[8];   // MODE 3 family: canonical chunk c = segments [cb[c], cb[c+1]) of a warp's pass list (sym64_chunks)
+    // rasteriser constants the host can round exactly like numpy does
+    double step_y, inv_y; // (2 HEIGHT - 0) / G and its reciprocal
+    double inv_x;         // ~ G / WIDTH: only seeds the bin guess (count_le settles ties against the exact edges)
+    double inv_P, inv_G;  // correctly rounded 1/(N+A) and 1/G: exact quotients by one FMA correction (div_by_const)
 };
 
 // One STAGE buffer = what is prefetched for the step of one env (the locust noise row follows
@@ -73,6 +84,7 @@ struct Smem {
                       //   MODE 1/3: nt 32-tiles x 64 (each tile stored twice: wrap-free lane+k reads) + A agents
                       //   MODE 2/4: N locusts + A agents
     float2* slot;     // MODE 1/3: nt x nslots x 32 reaction-force partial sums
+    float2* own;      // MODE 3 with KS > 1: KS x (nt2 x 64) own-force partial sums of the warps sharing a super-tile
     // ---- rasteriser (present when the kernel rasterises)
     double2* rx;      // N+A: post-step positions handed from the force to the raster group
     int* mail;        // [0] env id handed to the raster group (-1 = no more), [1] next env grabbed from the work queue
@@ -84,6 +96,51 @@ struct Smem {
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
 __host__ __device__ inline int n_tiles(int N) { return (N + 31) >> 5; }
+
+// ---- canonical decomposition of the MODE 3 pair work (64-wide super-tiles) ---------------------------------------
+// A warp's work on its super-tile is a list of SEGMENTS (a run of lane-rotation steps against one half-tile, with
+// its own reaction slot); the list is cut into FOUR canonical chunks of about equal length.  Own forces are summed
+// per chunk and combined as (c0 + c1) + (c2 + c3), whoever computes them: one warp (KS = 1), two warps taking two
+// chunks each (KS = 2) or four warps taking one each (KS = 4).  The results are therefore bitwise independent of
+// KS, which the host picks by batch size (few envs -> more warps per env).
+//   N <= 64 (one super-tile, two passes of 15 steps): segments of <= 8 steps (2 per pass) so that there are 4;
+//   else: a segment is a whole pass (15 / 32 / 16 steps).
+__host__ __device__ inline int sym64_seg(int N) { return N <= 64 ? 8 : 32; }
+__host__ __device__ inline int sym64_qmax(int N) { return N <= 64 ? 2 : 1; }
+__host__ __device__ inline int sym64_nslots(int N) { return 1 + ((N + 63) >> 6) / 2; }
+__host__ __device__ inline int sym64_nseg(int N) { return 2 * sym64_nslots(N) * sym64_qmax(N); }
+// rotation steps of pass pair o (both passes of a pair have the same length)
+__host__ __device__ inline int sym64_pass_steps(int N, int o) {
+    const int nt2 = (N + 63) >> 6, nfull = (nt2 - 1) >> 1;
+    return o == 0 ? 15 : (o <= nfull ? 32 : 16);
+}
+// pair evaluations of segment s (the own-tile passes carry two extra single pairs)
+__host__ __device__ inline int sym64_seg_steps(int N, int s) {
+    const int qmax = sym64_qmax(N), seg = sym64_seg(N);
+    const int p = s / qmax, q = s % qmax, n = sym64_pass_steps(N, p >> 1);
+    int k = n - q * seg;
+    k = k < 0 ? 0 : (k > seg ? seg : k);
+    if (p < 2 && (q == 0 || q == qmax - 1)) k += 1;
+    return k;
+}
+// chunk boundaries cb[0..4]: boundary j sits where the running step count is nearest to j/4 of the total
+inline void sym64_chunks(int N, unsigned char cb[8]) {
+    const int ns = sym64_nseg(N);
+    int total = 0;
+    for (int s = 0; s < ns; ++s) total += sym64_seg_steps(N, s);
+    cb[0] = 0;
+    for (int j = 1; j < 4; ++j) {
+        int best = cb[j - 1], cum = 0, bestd = 1 << 30;
+        for (int s = 0; s <= ns; ++s) {
+            const int d = 4 * cum - j * total;
+            if (s >= cb[j - 1] && (d < 0 ? -d : d) < bestd) { bestd = d < 0 ? -d : d; best = s; }
+            if (s < ns) cum += sym64_seg_steps(N, s);
+        }
+        cb[j] = (unsigned char)best;
+    }
+    cb[4] = (unsigned char)ns;
+    cb[5] = cb[6] = cb[7] = 0;
+}
 
 __host__ __device__ inline size_t smem_stage_bytes(int N, int A) { return 16 * ((size_t)N + 3 * A + 1); }
 __host__ __device__ inline int sym_tiles(int N, int sym);
@@ -100,22 +157,30 @@ __host__ __device__ inline bool table_is16(int N, int A) { return N < (1 << kAge
 __host__ __device__ inline size_t smem_table_bytes(int N, int A, int G) {
     return table_is16(N, A) ? smem_align(sizeof(uint16_t) * G * G) : smem_align(sizeof(uint32_t) * G * G);
 }
-// sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3)
+// sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3 family)
 __host__ __device__ inline int sym_tiles(int N, int sym) { return sym == 2 ? 2 * ((N + 63) >> 6) : n_tiles(N); }
 __host__ __device__ inline int sym_slots(int N, int sym) {
-    return sym == 2 ? 1 + ((N + 63) >> 6) / 2 : 1 + n_tiles(N) / 2;
+    return sym == 2 ? sym64_nslots(N) * sym64_qmax(N) : 1 + n_tiles(N) / 2;
 }
-__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym) {
-    return smem_src_bytes(N, A, sym) +
-           (sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * sym_slots(N, sym) * 32) : 0);
+__host__ __device__ inline size_t smem_slot_bytes(int N, int sym) {
+    return sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * sym_slots(N, sym) * 32) : 0;
 }
-__host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G) {
-    return smem_align(sizeof(double2) * (N + A)) + smem_table_bytes(N, A, G) + smem_align(sizeof(int) * (N + A));
+__host__ __device__ inline size_t smem_own_bytes(int N, int sym, int ks) {
+    return (sym == 2 && ks > 1) ? smem_align(sizeof(float2) * ks * sym_tiles(N, sym) * 32) : 0;
+}
+__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym, int ks) {
+    return smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) + smem_own_bytes(N, sym, ks);
+}
+// raster: 0 none, 1 raster group with its own point buffer, 2 the force group rasterises (points = stage buffer)
+__host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G, int raster) {
+    if (!raster) return 0;
+    return (raster == 1 ? smem_align(sizeof(double2) * (N + A)) : 0) + smem_table_bytes(N, A, G) +
+           smem_align(sizeof(int) * (N + A));
 }
 // n_stage: stage buffers (2 in the pipelined step kernel, 1 in reset/forces, 0 in the rasteriser)
-__host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, bool raster, int sym) {
-    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(N, A) + (force ? smem_force_bytes(N, A, sym) : 0) +
-           (raster ? smem_raster_bytes(N, A, G) : 0);
+__host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, int raster, int sym, int ks) {
+    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(N, A) + (force ? smem_force_bytes(N, A, sym, ks) : 0) +
+           smem_raster_bytes(N, A, G, raster);
 }
 
 __device__ __forceinline__ Stage stage_at(unsigned char* base, int N, int A, int b) {
@@ -129,7 +194,8 @@ __device__ __forceinline__ Stage stage_at(unsigned char* base, int N, int A, int
     return s;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, int n_stage, bool force, int sym) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, int n_stage, bool force, int sym, int ks,
+                                      int raster) {
     Smem s;
     s.st = stage_at(base, N, A, 0);
     size_t o = (size_t)n_stage * smem_stage_bytes(N, A);
@@ -140,11 +206,26 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     s.mail = reinterpret_cast<int*>(base + o);    o += 16;
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
-    if (force) o += smem_force_bytes(N, A, sym);
-    s.rx = reinterpret_cast<double2*>(base + o);    o += smem_align(sizeof(double2) * (N + A));
+    s.own = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym));
+    if (force) o += smem_force_bytes(N, A, sym, ks);
+    s.rx = reinterpret_cast<double2*>(base + o);
+    if (raster == 1) o += smem_align(sizeof(double2) * (N + A));
     s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_table_bytes(N, A, G);
     s.cid = reinterpret_cast<int*>(base + o);
     return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Debug timeline (swarm_debug_trace): record `rec` holds, for phase ph < 8, the global timer (ns) in word 2 ph and the
+// SM's cycle counter in word 2 ph + 1.  One uniform, never-taken branch per call site in production.
+enum : int { TR_ENTRY = 0, TR_LOADED = 1, TR_FORCES = 2, TR_STEPPED = 3, TR_STORED = 4, TR_RASTER = 5, TR_MEAN = 6, TR_DONE = 7 };
+__device__ __forceinline__ void trace_mark(const KP& kp, const long long rec, const int ph) {
+    if (kp.trace != nullptr && rec < kp.trace_slots) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        kp.trace[rec * 16 + 2 * ph] = t;
+        kp.trace[rec * 16 + 2 * ph + 1] = (unsigned long long)clock64();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -244,17 +325,27 @@ __device__ __forceinline__ float4 split_hilo(const double2 p, const double c) {
 // MODE: 1 = unordered pairs, a warp owns a 32-locust tile, 1 target per lane
 //       3 = unordered pairs, a warp owns a 64-locust super-tile, 2 targets per lane (half the
 //           shared-memory loads and shuffles per pair; used when N pads to 64 as well as to 32)
+//       5, 6 = MODE 3 with KS = 2 / 4 warps per super-tile (each takes 2 / 1 of the four canonical chunks of the pass
+//           list; afterwards a thread finishes and integrates ONE target): for batches too small to fill the SMs
 //       2/4 = ordered pairs, 2/4 targets per thread (N > 512)
 template <int MODE>
 struct ModeT {
-    static constexpr int T = MODE == 1 ? 1 : (MODE == 3 ? 2 : MODE);
-    static constexpr int SYM = MODE == 1 ? 1 : (MODE == 3 ? 2 : 0);
+    static constexpr int T = (MODE == 1 || MODE == 5 || MODE == 6) ? 1 : (MODE == 3 ? 2 : MODE);
+    static constexpr int SYM = MODE == 1 ? 1 : ((MODE == 3 || MODE == 5 || MODE == 6) ? 2 : 0);
+    static constexpr int KS = MODE == 5 ? 2 : (MODE == 6 ? 4 : 1);
 };
 
-// locust owned by thread g.tid as its t-th target
+constexpr int kNoTarget = 0x7fffffff;
+
+// locust owned by thread g.tid as its t-th target (kNoTarget: none -- the third and fourth warp of a KS = 4 team)
 template <int MODE>
-__device__ __forceinline__ int target_index(const Grp& g, int t) {
-    return MODE == 3 ? ((g.tid >> 5) * 64 + t * 32 + (g.tid & 31)) : g.tid + t * g.n;
+__device__ __forceinline__ int target_index(const Grp& g, int t, const KP& kp) {
+    if constexpr (MODE == 3) return (g.tid >> 5) * 64 + t * 32 + (g.tid & 31);
+    if constexpr (MODE == 5 || MODE == 6) {
+        const int nt2 = (kp.N + 63) >> 6, W = g.tid >> 5, cg = W / nt2, I = W - cg * nt2;
+        return cg < 2 ? (2 * I + cg) * 32 + (g.tid & 31) : kNoTarget;
+    }
+    return g.tid + t * g.n;
 }
 
 template <int MODE>
@@ -496,93 +587,159 @@ __device__ __forceinline__ void tile_sym2(const float4* __restrict__ tl, const i
     }
 }
 
-// MODE 3, part 1.  Warp I owns super-tile I = half-tiles 2I (A targets) and 2I+1 (B targets).
-// Passes (one loop, so the pair code exists once):
+// MODE 3 family, part 1.  Super-tile I = half-tiles 2I (A targets) and 2I+1 (B targets); its work is the pass list
 //   p = 0  own A half as sources: offset 0 (B target only: the A x B block is split by offset, (B target,
 //          A source) takes 0..15), offsets 1..15 both targets, offset 16 A target one way;
 //   p = 1  own B half as sources: offsets 1..15 both targets, offset 16 A target ((A target, B source)
 //          takes 1..16) with reaction + B target one way;
 //   then   super-tiles I+1 .. I+floor((nt2-1)/2): both halves, all 32 offsets;
-//          super-tile I+nt2/2 (nt2 even): both halves, half the offsets each way.
-template <bool PRECISE>
-__device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
-                                                   float (&vy)[2]) {
-    const int lane = g.tid & 31, I = g.tid >> 5;
+//          super-tile I+nt2/2 (nt2 even): both halves, half the offsets each way,
+// cut into segments and four canonical chunks (sym64_chunks).  With KS warps per super-tile, warp (I, cg) runs the
+// chunks [cg * 4/KS, (cg + 1) * 4/KS); one loop over the segments, so the pair code exists once.  On return (ax, ay)
+// hold this thread's share of the own forces of its two targets, combined in the canonical order.
+template <int KS, bool PRECISE>
+__device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp, const Grp& g, float (&ax)[2],
+                                                   float (&ay)[2]) {
+    const int lane = g.tid & 31, W = g.tid >> 5;
     const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
+    const int cg = KS == 1 ? 0 : W / nt2, I = KS == 1 ? W : W - cg * nt2;
     const int nxt = (lane + 1) & 31;
     const int nfull = (nt2 - 1) >> 1;
-    const int npass = 2 * nslots;
+    const int qmax = sym64_qmax(kp.N), seg = sym64_seg(kp.N);
     const float4* S = sm.src;
     const float4 tgA = S[(2 * I) * 64 + lane], tgB = S[(2 * I + 1) * 64 + lane];
-    float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f;
+    constexpr int CH = 4 / KS;                        // canonical chunks run by this thread
+    float tAx = 0.f, tAy = 0.f, tBx = 0.f, tBy = 0.f;      // (c0 + c1) [+ (c2 + c3)]
+    float uAx = 0.f, uAy = 0.f, uBx = 0.f, uBy = 0.f;      // c_even [+ c_odd]
 #pragma unroll 1
-    for (int p = 0; p < npass; ++p) {
-        const int o = p >> 1, h = p & 1;
-        int J = I, first = 1, n = 15;
-        if (o > 0) {
-            if (o <= nfull) {
-                J = I + o;
-                if (J >= nt2) J -= nt2;
-                first = 0;
-                n = 32;
+    for (int c = 0; c < CH; ++c) {
+        const int cc = cg * CH + c;
+        float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f;
+#pragma unroll 1
+        for (int s = kp.cb[cc]; s < (int)kp.cb[cc + 1]; ++s) {
+            const int p = qmax == 2 ? s >> 1 : s, q = qmax == 2 ? s & 1 : 0;
+            const int o = p >> 1, h = p & 1;
+            int J = I, first = 1, n = 15;
+            if (o > 0) {
+                if (o <= nfull) {
+                    J = I + o;
+                    if (J >= nt2) J -= nt2;
+                    first = 0;
+                    n = 32;
+                } else {
+                    J = I < o ? I + o : I - o;
+                    first = I < o ? 0 : 1;
+                    n = 16;
+                }
+            }
+            const int f = first + q * seg;                                  // this segment: offsets f .. f + nn - 1
+            const int nn = (n - q * seg) < seg ? (n - q * seg) : seg;
+            const bool tail = (q + 1) * seg >= n;                           // the pass ends with this segment
+            const int H = 2 * J + h;
+            const float4* tl = S + H * 64 + lane;
+            float bx = 0.f, by = 0.f;
+            if (p == 0 && q == 0) pair_sym<true, PRECISE>(tl[0], tgB, kp, aBx, aBy, bx, by);
+            tile_sym2<PRECISE>(tl + f, nn, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+            int last = f + nn - 1;                       // offset of the element whose reaction this lane holds
+            if (tail && p == 0) {
+                float ux, uy;
+                pair_sym<false, PRECISE>(tl[16], tgA, kp, aAx, aAy, ux, uy);
+            } else if (tail && p == 1) {
+                bx = __shfl_sync(kFull, bx, nxt);
+                by = __shfl_sync(kFull, by, nxt);
+                const float4 qq = tl[16];
+                float ux, uy;
+                pair_sym<true, PRECISE>(qq, tgA, kp, aAx, aAy, bx, by);
+                pair_sym<false, PRECISE>(qq, tgB, kp, aBx, aBy, ux, uy);
+                last = 16;
+            }
+            sm.slot[((H * nslots + o) * qmax + q) * 32 + ((lane + last) & 31)] = make_float2(bx, by);
+        }
+        if ((c & 1) == 0) {
+            uAx = aAx; uAy = aAy; uBx = aBx; uBy = aBy;
+        } else {
+            uAx += aAx; uAy += aAy; uBx += aBx; uBy += aBy;
+        }
+        if (c == CH - 1 || (c & 1)) {
+            if (c < 2) {
+                tAx = uAx; tAy = uAy; tBx = uBx; tBy = uBy;
             } else {
-                J = I < o ? I + o : I - o;
-                first = I < o ? 0 : 1;
-                n = 16;
+                tAx += uAx; tAy += uAy; tBx += uBx; tBy += uBy;
             }
         }
-        const int H = 2 * J + h;
-        const float4* tl = S + H * 64 + lane;
-        float bx = 0.f, by = 0.f;
-        if (p == 0) pair_sym<true, PRECISE>(tl[0], tgB, kp, aBx, aBy, bx, by);
-        tile_sym2<PRECISE>(tl + first, n, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-        int last = first + n - 1;                        // offset of the element whose reaction this lane holds
-        if (p == 0) {
-            float ux, uy;
-            pair_sym<false, PRECISE>(tl[16], tgA, kp, aAx, aAy, ux, uy);
-        } else if (p == 1) {
-            bx = __shfl_sync(kFull, bx, nxt);
-            by = __shfl_sync(kFull, by, nxt);
-            const float4 q = tl[16];
-            float ux, uy;
-            pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
-            pair_sym<false, PRECISE>(q, tgB, kp, aBx, aBy, ux, uy);
-            last = 16;
-        }
-        sm.slot[(H * nslots + o) * 32 + ((lane + last) & 31)] = make_float2(bx, by);
     }
-    vx[0] = aAx; vy[0] = aAy; vx[1] = aBx; vy[1] = aBy;
+    ax[0] = tAx; ay[0] = tAy; ax[1] = tBx; ay[1] = tBy;
+    if constexpr (KS > 1) {      // hand the partial sums to the threads that finish the targets
+        float2* own = sm.own + (size_t)cg * nt2 * 64;
+        own[(2 * I) * 32 + lane] = make_float2(tAx, tAy);
+        own[(2 * I + 1) * 32 + lane] = make_float2(tBx, tBy);
+    }
 }
 
-// MODE 3, part 2: reactions (fixed order: bitwise reproducible) and the agents' pull.
-template <bool PRECISE>
-__device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
-                                                    float (&vy)[2]) {
-    const int lane = g.tid & 31, I = g.tid >> 5;
+// reactions received by half-tile H (fixed order: bitwise reproducible), added to (vx, vy)
+__device__ __forceinline__ void sym64_add_reactions(const Smem& sm, const KP& kp, const int H, const int lane, float& vx,
+                                                    float& vy) {
     const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
+    const int qmax = sym64_qmax(kp.N), seg = sym64_seg(kp.N);
     for (int o = 0; o < nslots; ++o) {
-        const float2 ra = sm.slot[((2 * I) * nslots + o) * 32 + lane];
-        const float2 rb = sm.slot[((2 * I + 1) * nslots + o) * 32 + lane];
-        vx[0] += ra.x; vy[0] += ra.y;
-        vx[1] += rb.x; vy[1] += rb.y;
+        const int nq = qmax == 1 ? 1 : (sym64_pass_steps(kp.N, o) + seg - 1) / seg;
+        for (int q = 0; q < nq; ++q) {
+            const float2 r = sm.slot[((H * nslots + o) * qmax + q) * 32 + lane];
+            vx += r.x;
+            vy += r.y;
+        }
     }
-    const float4 tgA = sm.src[(2 * I) * 64 + lane], tgB = sm.src[(2 * I + 1) * 64 + lane];
+}
+
+// MODE 3 family, part 2: own partial sums, reactions (fixed order) and the agents' pull.
+// KS = 1: (vx, vy)[2] come in as the own forces of the lane's two targets.  KS > 1: the thread finishes ONE target
+// (target_index), gathers the own partial sums of the KS warps from shared memory; result in (vx, vy)[0].
+template <int KS, bool PRECISE>
+__device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp, const Grp& g, float* vx, float* vy) {
+    const int lane = g.tid & 31, W = g.tid >> 5;
+    const int nt2 = (kp.N + 63) >> 6;
     const float4* ag = sm.src + nt2 * 128;      // agents act on locusts only (multiagent.py:108-113)
-    if constexpr (PRECISE) {
-        for (int k = 0; k < kp.A; ++k) {
-            const float4 q = ag[k];
-            pair_ordered<PRECISE>(q, tgA, kp, vx[0], vy[0]);
-            pair_ordered<PRECISE>(q, tgB, kp, vx[1], vy[1]);
+    if constexpr (KS == 1) {
+        const int I = W;
+        sym64_add_reactions(sm, kp, 2 * I, lane, vx[0], vy[0]);
+        sym64_add_reactions(sm, kp, 2 * I + 1, lane, vx[1], vy[1]);
+        const float4 tgA = sm.src[(2 * I) * 64 + lane], tgB = sm.src[(2 * I + 1) * 64 + lane];
+        if constexpr (PRECISE) {
+            for (int k = 0; k < kp.A; ++k) {
+                const float4 q = ag[k];
+                pair_ordered<PRECISE>(q, tgA, kp, vx[0], vy[0]);
+                pair_ordered<PRECISE>(q, tgB, kp, vx[1], vy[1]);
+            }
+        } else {
+            const Targets2 t = make_targets2(tgA, tgB);
+            const PairConst2 c = make_pair_const2(kp);
+            f32x2 naA = pk2(-vx[0], -vy[0]), naB = pk2(-vx[1], -vy[1]), b = 0;
+#pragma unroll 2
+            for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
+            upk2(naA, vx[0], vy[0]);
+            upk2(naB, vx[1], vy[1]);
+            vx[0] = -vx[0]; vy[0] = -vy[0]; vx[1] = -vx[1]; vy[1] = -vy[1];
         }
     } else {
-        const Targets2 t = make_targets2(tgA, tgB);
-        const PairConst2 c = make_pair_const2(kp);
-        f32x2 naA = pk2(-vx[0], -vy[0]), naB = pk2(-vx[1], -vy[1]), b = 0;
+        const int cg = W / nt2, I = W - cg * nt2;
+        vx[0] = 0.f;
+        vy[0] = 0.f;
+        if (cg >= 2) return;
+        const int H = 2 * I + cg, slot = H * 32 + lane;
+        const float2 o0 = sm.own[slot], o1 = sm.own[(size_t)nt2 * 64 + slot];
+        float x = o0.x + o1.x, y = o0.y + o1.y;
+        if constexpr (KS == 4) {
+            const float2 o2 = sm.own[(size_t)2 * nt2 * 64 + slot], o3 = sm.own[(size_t)3 * nt2 * 64 + slot];
+            x += o2.x + o3.x;
+            y += o2.y + o3.y;
+        }
+        sym64_add_reactions(sm, kp, H, lane, x, y);
+        const float4 tg = sm.src[H * 64 + lane];
+        // scalar pairs: operation for operation the roundings of pair2_fast (negation is exact)
 #pragma unroll 2
-        for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
-        upk2(naA, vx[0], vy[0]);
-        upk2(naB, vx[1], vy[1]);
-        vx[0] = -vx[0]; vy[0] = -vy[0]; vx[1] = -vx[1]; vy[1] = -vy[1];
+        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, x, y);
+        vx[0] = x;
+        vy[0] = y;
     }
 }
 
@@ -607,42 +764,68 @@ __device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, con
 }
 
 // SwarmEnv.v_calculate (multiagent.py:88-115) on staged sources: v of this thread's targets (wind
-// and gravity added, before any cutoff) and its share of sum_j |v_j|^2.  Needs the staged sources
-// visible (a barrier since stage_*); contains one group barrier in MODE 1.
+// and gravity added, before any cutoff).  Needs the staged sources visible (a barrier since stage_*);
+// contains one group barrier in the unordered-pair modes.
 template <int MODE, bool PRECISE>
-__device__ __forceinline__ double pair_forces(const Smem& sm, const KP& kp, const Grp& g,
-                                              float (&vx)[ModeT<MODE>::T], float (&vy)[ModeT<MODE>::T]) {
+__device__ __forceinline__ void pair_forces(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[ModeT<MODE>::T],
+                                            float (&vy)[ModeT<MODE>::T]) {
     constexpr int T = ModeT<MODE>::T;
     if constexpr (MODE == 1) {
         forces_sym_tiles<PRECISE>(sm, kp, g, vx[0], vy[0]);
         g.sync();
         forces_sym_finish<PRECISE>(sm, kp, g, vx[0], vy[0]);
     } else if constexpr (MODE == 3) {
-        forces_sym64_tiles<PRECISE>(sm, kp, g, vx, vy);
+        forces_sym64_tiles<1, PRECISE>(sm, kp, g, vx, vy);
         g.sync();
-        forces_sym64_finish<PRECISE>(sm, kp, g, vx, vy);
+        forces_sym64_finish<1, PRECISE>(sm, kp, g, vx, vy);
+    } else if constexpr (MODE == 5 || MODE == 6) {
+        float ax[2], ay[2];
+        forces_sym64_tiles<ModeT<MODE>::KS, PRECISE>(sm, kp, g, ax, ay);
+        g.sync();
+        forces_sym64_finish<ModeT<MODE>::KS, PRECISE>(sm, kp, g, vx, vy);
     } else {
         forces_ordered<T, PRECISE>(sm, kp, g, vx, vy);
     }
-    double e = 0.0;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         vx[t] += kp.U;
         vy[t] += kp.Gv;
-        if (target_index<MODE>(g, t) < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
     }
-    return e;
 }
 
-// reward = -mean_j |v_j|^2 from the per-thread shares: warp shuffle, then one slot per warp.  The
-// caller barriers between energy_put and energy_get.
-__device__ __forceinline__ void energy_put(const Smem& sm, const Grp& g, double e) {
-    e = warp_sum(e);
-    if ((g.tid & 31) == 0) sm.red[g.tid >> 5] = e;
+// reward = -mean_j |v_j|^2 (multiagent.py:114-115, v before any cutoff): a warp-shuffle sum per 32-locust tile
+// into one slot per tile, then the slots in order -- the same tree whichever mode / KS computed the forces.
+// The caller barriers between energy_put and energy_get.
+template <int MODE>
+__device__ __forceinline__ int energy_slots(const KP& kp, const Grp& g) {
+    return ModeT<MODE>::SYM == 2 ? 2 * ((kp.N + 63) >> 6) : (g.n >> 5);
 }
+template <int MODE>
+__device__ __forceinline__ void energy_put(const Smem& sm, const KP& kp, const Grp& g, const float (&vx)[ModeT<MODE>::T],
+                                           const float (&vy)[ModeT<MODE>::T]) {
+    constexpr int T = ModeT<MODE>::T;
+    if constexpr (ModeT<MODE>::SYM == 2) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = target_index<MODE>(g, t, kp);
+            if (j == kNoTarget) continue;          // warp-uniform
+            double e = j < kp.N ? (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t] : 0.0;
+            e = warp_sum(e);
+            if ((g.tid & 31) == 0) sm.red[j >> 5] = e;
+        }
+    } else {
+        double e = 0.0;
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+            if (target_index<MODE>(g, t, kp) < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
+        e = warp_sum(e);
+        if ((g.tid & 31) == 0) sm.red[g.tid >> 5] = e;
+    }
+}
+template <int MODE>
 __device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const Grp& g) {
     double tot = 0.0;
-    const int nw = g.n >> 5;
+    const int nw = energy_slots<MODE>(kp, g);
     for (int w = 0; w < nw; ++w) tot += sm.red[w];   // same order in every thread
     return -tot / (double)kp.N;
 }
@@ -651,15 +834,16 @@ __device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const
 // element written by the thread that owns it here (element i <-> thread i mod n) or visible through
 // a barrier.  Postcondition: state updated and visible to the whole group; returns the reward.
 template <int MODE, bool PRECISE>
-__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const Grp& g, float* v_out) {
+__device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const Grp& g, float* v_out, const double wind_a,
+                                           const long long trace_rec = -1) {
     constexpr int T = ModeT<MODE>::T;
-    // multiagent.py:33-38  agents move first: v_action (+wind on x) through x_update; the mover
-    // stages the agent's NEW position as a force source (multiagent.py:39: old x, new xa)
+    // multiagent.py:33-38  agents move first: v_action (+wind on x unless add_wind=False) through x_update; the
+    // mover stages the agent's NEW position as a force source (multiagent.py:39: old x, new xa)
     float4* ag = agent_sources<MODE>(sm, kp);
     for (int k = g.tid; k < kp.A; k += g.n) {
         double2 a = sm.st.as[k];
         double2 w = sm.act[k];
-        w.x = __dadd_rn(w.x, kp.wind);
+        w.x = __dadd_rn(w.x, wind_a);
         move_particle(a, w, sm.st.an[k], kp.dt, kp.sigma);
         sm.st.as[k] = a;
         ag[k] = split_hilo(a, kp.cscale);
@@ -667,13 +851,14 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
     stage_locusts<MODE>(sm, kp, g);
     g.sync();
     float vx[T], vy[T];
-    const double e = pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
-    energy_put(sm, g, e);
+    pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
+    if (trace_rec >= 0 && g.tid == 0) trace_mark(kp, trace_rec, TR_FORCES);
+    energy_put<MODE>(sm, kp, g, vx, vy);
     cp_async_wait_but_one();   // this thread's own noise rows have landed in sm.nx (no-op outside k_step)
     // multiagent.py:40  locusts move with the pre-cutoff v just computed
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const int j = target_index<MODE>(g, t);
+        const int j = target_index<MODE>(g, t, kp);
         if (j < kp.N) {
             if (v_out) reinterpret_cast<float2*>(v_out)[j] = make_float2(vx[t], vy[t]);
             double2 p = sm.st.xs[j];
@@ -682,7 +867,7 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
         }
     }
     g.sync();
-    return energy_get(sm, kp, g);
+    return energy_get<MODE>(sm, kp, g);
 }
 
 // SwarmEnv._reset (multiagent.py:46-63) for env e on the stage buffer, in two pieces so that the
@@ -809,7 +994,8 @@ __device__ __forceinline__ void tma_zero_fill_wait_done() {
 }
 
 // One-time clear of the counter table (afterwards env_raster leaves it clean).
-__device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, const RGrp& g) {
+template <typename Group>
+__device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, const Group& g) {
     for (int i = g.tid; i < words; i += g.n) sm.table[i] = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA zero fill reads these zeros
 }
@@ -822,29 +1008,54 @@ __device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, co
 // early_release_fn() is called by every thread once it has read its last point from pts (the step
 // kernel hands the buffer back to the force group there).
 struct NoRelease { __device__ __forceinline__ void operator()() const {} };
-template <typename Release>
-__device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const RGrp& g,
+
+// a / b for a divisor whose correctly rounded reciprocal inv_b = RN(1 / b) the host supplies: q0 = RN(a inv_b) is within
+// one ulp, the FMA residual r = a - q0 b is exact and RN(q0 + r inv_b) is the correctly rounded quotient (Markstein
+// 1990) -- three FP64 operations instead of the ~40-instruction division routine.  Outside the range where the
+// residual is exact (quotients near the subnormals / overflow) the plain division is used.
+__device__ __forceinline__ double div_by_const(const double a, const double b, const double inv_b) {
+    const double m = fabs(a);
+    if (!(m > 1e-280 && m < 1e280)) return a / b;
+    const double q0 = __dmul_rn(a, inv_b);
+    const double r = __fma_rn(-q0, b, a);
+    return __fma_rn(r, inv_b, q0);
+}
+
+template <typename Group, typename Release>
+__device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const Group& g,
                                            float* __restrict__ grid_e, uint8_t* __restrict__ pos_e, const bool tma,
-                                           const Release early_release_fn) {
+                                           const Release early_release_fn, const long long trace_rec = -1) {
     const int N = kp.N, A = kp.A, G = kp.G, P = N + A;
     const bool t16 = table_is16(N, A);
+    if (trace_rec >= 0 && g.tid == 0) trace_mark(kp, trace_rec, TR_RASTER);
     // phase 0: one thread walks the sequential FP64 mean (np.mean(vstack([x,xa]),axis=0)[0] is a
-    // plain left-to-right sum, ~23 cycles per dependent DADD)
+    // plain left-to-right sum, one dependent DADD per element)
     if (g.tid == 0) {
         double s = 0.0;
 #pragma unroll 8
         for (int i = 0; i < P; ++i) s = __dadd_rn(s, pts[i].x);
-        sm.box[0] = s / (double)P;
+        sm.box[0] = div_by_const(s, (double)P, kp.inv_P);
+        if (trace_rec >= 0) trace_mark(kp, trace_rec, TR_MEAN);
         if (tma) tma_zero_fill_wait_read();      // the table may be written from here on
     }
     g.sync();
     // phase 1: bin every point in FP64 against numpy's edges, count with warp-aggregated atomics
     const double m = sm.box[0];
     const double lo_x = m - kp.half_w, hi_x = m + kp.half_w;
-    const double step_x = (hi_x - lo_x) / (double)G;
+    const double step_x = div_by_const(hi_x - lo_x, (double)G, kp.inv_G);
     const double lo_y = 0.0, hi_y = kp.y_hi;
-    const double step_y = (hi_y - lo_y) / (double)G;
-    const double inv_x = 1.0 / step_x, inv_y = 1.0 / step_y;
+    const double step_y = kp.step_y;
+    // 1 / step_x seeds the bin guess: two Newton steps from the host's G / WIDTH (step_x differs from WIDTH / G by
+    // the rounding of mean +- WIDTH/2 only), a real division when the window sits absurdly far out
+    double inv_x = kp.inv_x;
+    const double dev = __fma_rn(-step_x, inv_x, 1.0);
+    if (fabs(dev) < 1e-4) {
+        inv_x = __fma_rn(inv_x, dev, inv_x);
+        inv_x = __fma_rn(inv_x, __fma_rn(-step_x, inv_x, 1.0), inv_x);
+    } else {
+        inv_x = 1.0 / step_x;
+    }
+    const double inv_y = kp.inv_y;
     for (int base = 0; base < P; base += g.n) {
         const int p = base + g.tid;
         uint32_t key = 0xffffffffu;
@@ -905,6 +1116,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
     }
     if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cleaned counters -> next TMA zero fill
     g.sync();
+    if (trace_rec >= 0 && g.tid == 0) trace_mark(kp, trace_rec, TR_DONE);
 }
 
 }  // namespace swarm

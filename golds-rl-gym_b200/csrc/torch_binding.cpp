@@ -52,10 +52,17 @@ SwarmState make_state(const SwarmParams& p, const at::Tensor& x, const at::Tenso
     need(noise_a, at::kDouble, {E, A, 2}, "noise_a");
     need(elapsed, at::kInt, {E}, "elapsed");
     need(episode, at::kInt, {E}, "episode");
-    if (work.has_value()) need(*work, at::kInt, {2 + E}, "work");
+    if (work.has_value()) {
+        TORCH_CHECK(work->is_cuda() && work->scalar_type() == at::kInt && work->is_contiguous() && work->dim() == 1,
+                    "work must be a contiguous 1-D int32 CUDA tensor");
+        TORCH_CHECK(work->get_device() == x.get_device(), "work is on another device than x");
+    }
+    for (const at::Tensor* t : {&xa, &noise_x, &noise_a, &elapsed, &episode})
+        TORCH_CHECK(t->get_device() == x.get_device(), "all state tensors must be on the same device");
     return SwarmState{x.data_ptr<double>(), xa.data_ptr<double>(), noise_x.data_ptr<double>(), noise_a.data_ptr<double>(),
                       elapsed.data_ptr<int32_t>(), reinterpret_cast<uint32_t*>(episode.data_ptr<int32_t>()),
-                      work.has_value() ? reinterpret_cast<uint32_t*>(work->data_ptr<int32_t>()) : nullptr};
+                      work.has_value() ? reinterpret_cast<uint32_t*>(work->data_ptr<int32_t>()) : nullptr,
+                      work.has_value() ? (uint64_t)work->numel() : 0};
 }
 
 SwarmStepIO make_io(const SwarmParams& p, const at::Tensor& actions, const c10::optional<at::Tensor>& noise_a_step,
@@ -112,6 +119,10 @@ void op_step(const at::Tensor& params, at::Tensor x, at::Tensor xa, at::Tensor n
     c10::cuda::CUDAGuard guard(x.device());
     const SwarmState st = make_state(p, x, xa, noise_x, noise_a, elapsed, episode, work);
     const SwarmStepIO io = make_io(p, actions, noise_a_step, noise_x_step, reward, done, grid, positions, v_out, flags);
+    TORCH_CHECK(actions.get_device() == x.get_device() && reward.get_device() == x.get_device() &&
+                    done.get_device() == x.get_device() && (!grid.has_value() || grid->get_device() == x.get_device()) &&
+                    (!positions.has_value() || positions->get_device() == x.get_device()),
+                "step: all tensors must be on x's device");
     SwarmInjectedDraws dr;
     if (reset_draws.size()) dr = make_draws(p, reset_draws);
     check(swarm_step(&p, &st, &io, reset_draws.size() ? &dr : nullptr, stream_of(x)), "swarm_step");

@@ -24,6 +24,25 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _on(object):
+    """Make ``device`` the current CUDA device around a ctypes call (the C side launches on the CURRENT device;
+    the torch ops carry their own CUDAGuard).  Free when it already is."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 class InjectedDraws(object):
     """Device copies of one reset's random draws for the whole batch (SwarmInjectedDraws)."""
 
@@ -71,9 +90,10 @@ class BatchedSwarmEnv(object):
 
     def __init__(self, num_envs, n_locusts=None, n_agents=None, grid_size=84, max_episode_steps=128,
                  seed=0, env_id_offset=0, device=None, math_mode="fast", auto_reset=True, rasterize=True,
-                 binding="torch"):
+                 binding="torch", tuning=0):
         """binding: "torch" = the hot calls go through torch.ops.swarm_b200.* (the C ABI as a PyTorch
-        extension, csrc/torch_binding.cpp), "ctypes" = straight into the C ABI.  Same kernels either way."""
+        extension, csrc/torch_binding.cpp), "ctypes" = straight into the C ABI.  Same kernels either way.
+        tuning: SwarmParams.tuning (0 = automatic launch shape; anything else only changes speed, never bits)."""
         self.lib = nat.load()
         if binding not in ("torch", "ctypes"):
             raise ValueError("binding must be 'torch' or 'ctypes'")
@@ -89,7 +109,7 @@ class BatchedSwarmEnv(object):
         self.rasterize = bool(rasterize)
         self.params = nat.SwarmParams(
             n_envs=self.E, n_locusts=self.N, n_agents=self.A, grid_size=self.G, n_burn_in=self.N_BURN_IN,
-            max_episode_steps=int(max_episode_steps), math_mode={"fast": 0, "precise": 1}[math_mode], reserved=0,
+            max_episode_steps=int(max_episode_steps), math_mode={"fast": 0, "precise": 1}[math_mode], tuning=int(tuning),
             noise=self.NOISE, gravity=self.GRAVITY, wind=self.WIND_SPEED, F=self.F, L=self.L, dt=self.dt,
             box_width=3.0, box_height=3.0, seed=int(seed) & (2 ** 64 - 1), env_id_offset=int(env_id_offset))
         nat.check(self.lib.swarm_validate(ctypes.byref(self.params)), "swarm_validate")
@@ -108,7 +128,7 @@ class BatchedSwarmEnv(object):
         self.grid = torch.zeros(E, G, G, 2, dtype=torch.float32, device=d)
         self.positions = torch.zeros(E, A, 2, dtype=torch.uint8, device=d)
         self.state_c = nat.SwarmState(_ptr(self.x), _ptr(self.xa), _ptr(self.noise_x), _ptr(self.noise_a),
-                                      _ptr(self.elapsed), _ptr(self.episode), _ptr(self.work))
+                                      _ptr(self.elapsed), _ptr(self.episode), _ptr(self.work), self.work.numel())
         self._io = nat.SwarmStepIO()
         self._io.reward, self._io.done = self.reward.data_ptr(), self.done_u8.data_ptr()
         self._grid_ptr, self._pos_ptr = self.grid.data_ptr(), self.positions.data_ptr()
@@ -117,6 +137,8 @@ class BatchedSwarmEnv(object):
         self._done_view = self.done_u8.view(torch.bool)
         self._io_host = None
         self._was_reset = False
+        self._blob_bytes, self._blob_t = None, None
+        self._ctx = _on(self.device)
         self.refresh_params()
 
     def refresh_params(self):
@@ -124,8 +146,12 @@ class BatchedSwarmEnv(object):
 
     @property
     def _blob(self):
-        """self.params (which callers may mutate, like the reference's class constants) packed for the torch ops."""
-        return nat.params_blob(self.params)
+        """self.params (which callers may mutate, like the reference's class constants) packed for the torch ops;
+        the CPU tensor is rebuilt only when the struct's bytes changed."""
+        b = bytes(self.params)
+        if b != self._blob_bytes:
+            self._blob_bytes, self._blob_t = b, nat.params_blob(self.params)
+        return self._blob_t
 
     # ------------------------------------------------------------------ gym surface
     def reset(self, mask=None, draws=None):
@@ -141,14 +167,15 @@ class BatchedSwarmEnv(object):
                 self.ops.reset(self._blob, *self._state_t[:6], m, draws.tensors() if draws is not None else [])
             self._was_reset = True
             return self.x, self.xa
-        nat.check(self.lib.swarm_reset(ctypes.byref(self.params), ctypes.byref(self.state_c), _ptr(m),
-                                       ctypes.byref(draws.c) if draws is not None else None,
-                                       _stream(self.device)), "swarm_reset")
+        with self._ctx:
+            nat.check(self.lib.swarm_reset(ctypes.byref(self.params), ctypes.byref(self.state_c), _ptr(m),
+                                           ctypes.byref(draws.c) if draws is not None else None,
+                                           _stream(self.device)), "swarm_reset")
         self._was_reset = True
         return self.x, self.xa
 
     def step(self, actions, noise_a=None, noise_x=None, clip=False, reset_draws=None, v_out=None,
-             rasterize=None, auto_reset=None, grid_out=None, positions_out=None):
+             rasterize=None, auto_reset=None, grid_out=None, positions_out=None, add_wind=True):
         """One env step for the whole batch; a single kernel launch.
 
         actions: (E,A,2) float32 or float64 CUDA tensor (float32 is the PAAC shared_actions dtype).
@@ -163,7 +190,8 @@ class BatchedSwarmEnv(object):
             raise ValueError("actions must be a contiguous (%d,%d,2) tensor on %s" % (self.E, self.A, self.device))
         rasterize = self.rasterize if rasterize is None else rasterize
         auto_reset = self.auto_reset if auto_reset is None else auto_reset
-        flags = (nat.SWARM_STEP_AUTO_RESET if auto_reset else 0) | (nat.SWARM_STEP_CLIP_ACTIONS if clip else 0)
+        flags = (nat.SWARM_STEP_AUTO_RESET if auto_reset else 0) | (nat.SWARM_STEP_CLIP_ACTIONS if clip else 0) | \
+                (0 if add_wind else nat.SWARM_STEP_NO_ACTION_WIND)
         if self.ops is not None:
             if actions.dtype not in (torch.float32, torch.float64):
                 raise ValueError("actions must be float32 or float64")
@@ -190,18 +218,20 @@ class BatchedSwarmEnv(object):
             io.grid, io.positions = None, None
         io.v_out = v_out.data_ptr() if v_out is not None else None
         io.flags = flags
-        rc = self.lib.swarm_step(self._params_ref, self._state_ref, self._io_ref,
-                                 ctypes.byref(reset_draws.c) if reset_draws is not None else None,
-                                 torch.cuda.current_stream(self.device).cuda_stream)
+        with self._ctx:
+            rc = self.lib.swarm_step(self._params_ref, self._state_ref, self._io_ref,
+                                     ctypes.byref(reset_draws.c) if reset_draws is not None else None,
+                                     torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             nat.check(rc, "swarm_step")
         return (self.x, self.xa), self.reward, self._done_view, {}
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) form
-    def step_host(self, host_actions, host_reward, host_done):
+    def step_host(self, host_actions, host_reward, host_done, host_grid=None, host_positions=None):
         """swarm_step_host: actions come from / reward+done go to HOST tensors; the observation stays in HBM
-        for the device-resident policy.  Synchronises the stream.  Pinned tensors are read / written by the
-        kernel itself over PCIe (zero-copy); self.reward / self.done_u8 are then NOT updated."""
+        for the device-resident policy unless host_grid / host_positions are given (then it is also copied back:
+        the numpy-out case of the reference's process_state).  Synchronises the stream.  Pinned tensors are read /
+        written by the kernel itself over PCIe (zero-copy); self.reward / self.done_u8 are then NOT updated."""
         io = self._io_host
         if io is None:
             io = self._io_host = nat.SwarmStepIO()
@@ -210,9 +240,12 @@ class BatchedSwarmEnv(object):
             self._io_host_ref = ctypes.byref(io)
         io.grid, io.positions = (self._grid_ptr, self._pos_ptr) if self.rasterize else (None, None)
         io.flags = nat.SWARM_STEP_AUTO_RESET if self.auto_reset else 0
-        rc = self.lib.swarm_step_host(self._params_ref, self._state_ref, self._io_host_ref, host_actions.data_ptr(),
-                                      host_reward.data_ptr(), host_done.data_ptr(),
-                                      torch.cuda.current_stream(self.device).cuda_stream)
+        with self._ctx:
+            rc = self.lib.swarm_step_host(self._params_ref, self._state_ref, self._io_host_ref, host_actions.data_ptr(),
+                                          host_reward.data_ptr(), host_done.data_ptr(),
+                                          host_grid.data_ptr() if host_grid is not None else None,
+                                          host_positions.data_ptr() if host_positions is not None else None,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             nat.check(rc, "swarm_step_host")
         return host_reward, host_done
@@ -223,8 +256,9 @@ class BatchedSwarmEnv(object):
         if self.ops is not None:
             self.ops.rasterize(self._blob, self.x, self.xa, self.grid, self.positions, box)
             return self.grid, self.positions
-        nat.check(self.lib.swarm_rasterize(ctypes.byref(self.params), _ptr(self.x), _ptr(self.xa), _ptr(self.grid),
-                                           _ptr(self.positions), _ptr(box), _stream(self.device)), "swarm_rasterize")
+        with self._ctx:
+            nat.check(self.lib.swarm_rasterize(ctypes.byref(self.params), _ptr(self.x), _ptr(self.xa), _ptr(self.grid),
+                                               _ptr(self.positions), _ptr(box), _stream(self.device)), "swarm_rasterize")
         return self.grid, self.positions
 
     def local_states(self, out=None):
@@ -234,8 +268,9 @@ class BatchedSwarmEnv(object):
         if self.ops is not None:
             self.ops.expand_obs(self._blob, self.grid, self.positions, out)
             return out
-        nat.check(self.lib.swarm_expand_obs(ctypes.byref(self.params), _ptr(self.grid), _ptr(self.positions),
-                                            _ptr(out), _stream(self.device)), "swarm_expand_obs")
+        with self._ctx:
+            nat.check(self.lib.swarm_expand_obs(ctypes.byref(self.params), _ptr(self.grid), _ptr(self.positions),
+                                                _ptr(out), _stream(self.device)), "swarm_expand_obs")
         return out
 
     def forces(self, x=None, xa=None, v=None, reward=None):
@@ -249,8 +284,9 @@ class BatchedSwarmEnv(object):
         if self.ops is not None:
             self.ops.forces(self._blob, x, xa, v, reward)
             return v, reward
-        nat.check(self.lib.swarm_forces(ctypes.byref(self.params), _ptr(x), _ptr(xa), _ptr(v), _ptr(reward),
-                                        _stream(self.device)), "swarm_forces")
+        with self._ctx:
+            nat.check(self.lib.swarm_forces(ctypes.byref(self.params), _ptr(x), _ptr(xa), _ptr(v), _ptr(reward),
+                                            _stream(self.device)), "swarm_forces")
         return v, reward
 
     def philox_draws(self):
@@ -260,8 +296,9 @@ class BatchedSwarmEnv(object):
         bufs = [torch.empty(E, N, 2, dtype=f64, device=d), torch.empty(E, A, 2, dtype=f64, device=d),
                 torch.empty(E, nb, A, 2, dtype=f64, device=d), torch.empty(E, nb + 1, A, 2, dtype=f64, device=d),
                 torch.empty(E, nb + 1, N, 2, dtype=f64, device=d)]
-        nat.check(self.lib.swarm_philox_draws(ctypes.byref(self.params), ctypes.byref(self.state_c),
-                                              *[_ptr(b) for b in bufs], _stream(self.device)), "swarm_philox_draws")
+        with self._ctx:
+            nat.check(self.lib.swarm_philox_draws(ctypes.byref(self.params), ctypes.byref(self.state_c),
+                                                  *[_ptr(b) for b in bufs], _stream(self.device)), "swarm_philox_draws")
         return InjectedDraws(*bufs, device=d)
 
     # ------------------------------------------------------------------ checkpointing
@@ -352,11 +389,9 @@ class SwarmEnv(object):
     def _step(self, v_action, add_wind=True):
         if self.states is None:
             raise TypeError("cannot unpack non-iterable NoneType object")   # multiagent.py:31 before reset
-        if not add_wind:
-            raise NotImplementedError("add_wind=False is never used by the reference callers")
         env = self._env
         a = torch.as_tensor(np.ascontiguousarray(v_action, dtype=np.float64)[None]).to(env.device)
-        _, reward, done, _ = env.step(a)
+        _, reward, done, _ = env.step(a, add_wind=bool(add_wind))      # multiagent.py:35-36
         self._sync_out()
         return self.states, np.float64(reward[0].item()), np.bool_(done[0].item()), {}
 
@@ -398,7 +433,7 @@ class SwarmEnv(object):
         x_t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)[None]).cuda()
         xa_t = torch.as_tensor(np.ascontiguousarray(xa, dtype=np.float64)[None]).cuda()
         p = nat.SwarmParams(n_envs=1, n_locusts=x_t.shape[1], n_agents=xa_t.shape[1], grid_size=84, n_burn_in=10,
-                            max_episode_steps=0, math_mode=0, reserved=0, noise=1e-4, gravity=float(G),
+                            max_episode_steps=0, math_mode=0, tuning=0, noise=1e-4, gravity=float(G),
                             wind=float(U), F=float(F), L=float(L), dt=0.05, box_width=3.0, box_height=3.0,
                             seed=0, env_id_offset=0)
         v = torch.empty(1, x_t.shape[1], 2, dtype=torch.float32, device=x_t.device)

@@ -9,7 +9,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name starts with `host_`;
  *   - the library allocates nothing, never synchronises (except the *_host call) and launches
- *     on the caller's stream; all entry points are thread-safe for distinct buffers/streams;
+ *     on the caller's stream; all entry points are thread-safe for distinct buffers AND distinct
+ *     streams (the two-kernel step keeps one internal side stream + fork/join event pair per
+ *     (device, caller stream); two host threads must not step on the SAME stream concurrently);
  *   - return value: 0 = ok, negative = SwarmStatus error (swarm_strerror);
  *   - layouts are C order.  x:(E,N,2) f64, xa:(E,A,2) f64, actions:(E,A,2),
  *     grid:(E,G,G,2) f32 indexed [env][x_bin][y_bin][channel], positions:(E,A,2) u8.
@@ -27,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SWARM_ABI_VERSION 2
+#define SWARM_ABI_VERSION 3
 
 /* opaque: a cudaStream_t passed as a pointer-sized handle (0 = legacy default stream) */
 typedef void* swarm_stream_t;
@@ -50,7 +52,10 @@ typedef struct SwarmParams {
     int32_t n_burn_in;          /* SwarmEnv.N_BURN_IN (10)                                  */
     int32_t max_episode_steps;  /* gym TimeLimit (128); 0 = raw SwarmEnv, no limit          */
     int32_t math_mode;          /* 0 = fast (MUFU rsqrt/ex2/rcp), 1 = precise (IEEE)        */
-    int32_t reserved;
+    int32_t tuning;             /* 0 = automatic launch shape.  Otherwise (tests / experiments; results are bitwise
+                                 * the same for every value): bits 0-2 = warps per 64-locust super-tile (1, 2, 4),
+                                 * bits 4-5 = rasteriser placement (1 follower kernel, 2 raster warps in the step
+                                 * kernel, 3 the step's own threads after the step)                            */
     double noise;               /* NOISE 1e-4   */
     double gravity;             /* GRAVITY -1   */
     double wind;                /* WIND_SPEED 1 */
@@ -73,11 +78,13 @@ typedef struct SwarmState {
     double* noise_a;            /* (E,A,2) unscaled N(0,1) */
     int32_t* elapsed;           /* (E) steps since reset   */
     uint32_t* episode;          /* (E) resets so far (Philox counter word) */
-    uint32_t* work;             /* nullable (2 + E): scratch words, ZERO when handed over and zero again after every
-                                 * call.  With them swarm_step produces the observation with a second kernel that
-                                 * follows the step on an internal higher-priority stream (per-env ready flags in
-                                 * work[2..]); without, with raster warps inside the step kernel (static env
-                                 * assignment).  Not shared between concurrently running calls. */
+    uint32_t* work;             /* nullable (work_words uint32): scratch words, ZERO when handed over and zero again
+                                 * after every call.  With at least 2 + E of them swarm_step may produce the
+                                 * observation with a second kernel that follows the step on an internal
+                                 * higher-priority stream (per-env ready flags in work[2..2+E)); with fewer (>= 2) it
+                                 * only uses the work queue work[0..1]; with none, static env assignment and raster
+                                 * warps inside the step kernel.  Not shared between concurrently running calls. */
+    uint64_t work_words;        /* number of uint32 words behind `work` (0 if work == NULL); checked, never trusted */
 } SwarmState;
 
 /* The reference's random draws of one reset (multiagent.py:51-56), injected for parity tests.
@@ -93,6 +100,10 @@ typedef struct SwarmInjectedDraws {
 #define SWARM_STEP_AUTO_RESET   1u  /* SwarmRunner._run: on done, reset and observe the new episode */
 #define SWARM_STEP_CLIP_ACTIONS 2u  /* SwarmRunner.transform_actions_for_env, in place on actions   */
 #define SWARM_STEP_ACTIONS_F64  4u  /* actions_f64 is used instead of actions_f32                   */
+#define SWARM_STEP_NO_ACTION_WIND 8u  /* SwarmEnv._step(add_wind=False), multiagent.py:30,35-36: the step's
+                                       * actions are used as they are (burn-in steps of an auto-reset still
+                                       * add the wind, like the reference's _reset -> step)                */
+#define SWARM_STEP_INKERNEL_RASTER 16u /* never use the follower kernel (see swarm_step); same results     */
 
 typedef struct SwarmStepIO {
     float* actions_f32;         /* (E,A,2) PAAC shared_actions dtype (paac.py:269); in/out if CLIP  */
@@ -129,6 +140,12 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
  * The call can be captured into a CUDA graph; instantiate such a graph with
  * cudaGraphInstantiateFlagUseNodePriority (PyTorch does), or the follower loses its priority
  * and runs after the step instead of next to it.
+ * The follower spins on per-env flags the step kernel raises, so the two kernels must be able to
+ * run side by side or step-first.  Eager launches guarantee it (the step is launched first); a tool
+ * that re-orders or isolates graph nodes (graph-node profiling, some debuggers) does not: pass
+ * SWARM_STEP_INKERNEL_RASTER or set the environment variable SWARM_B200_NO_FOLLOWER=1 there.  The
+ * spin is bounded (a follower that sees no progress for ~20 s traps: the call then fails with a
+ * CUDA launch error at the next synchronisation instead of hanging).
  * reset_draws: nullable; injected draws used by auto-reset instead of Philox. */
 int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                const SwarmInjectedDraws* reset_draws, swarm_stream_t stream);
@@ -138,10 +155,23 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
  * UVA) the kernel reads host_actions and writes host_reward / host_done directly over PCIe --
  * no staging copies (io->actions_f32 / io->reward / io->done are then left untouched).  With
  * pageable memory it copies host_actions to io->actions_f32, runs swarm_step and copies
- * io->reward / io->done back. */
+ * io->reward / io->done back.
+ * host_grid / host_positions: nullable (both or neither; need io->grid): the compact observation
+ * (E,G,G,2) f32 + (E,A,2) u8 is also copied back to the host (copy engine, after the step) -- the
+ * numpy-out case of the reference's process_state. */
 int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                     const float* host_actions, float* host_reward, uint8_t* host_done,
-                    swarm_stream_t stream);
+                    float* host_grid, uint8_t* host_positions, swarm_stream_t stream);
+
+/* Debug only: from now on every step / rasteriser kernel of this process records phase timestamps of each CTA's first
+ * env into device_words (n_words uint64, zeroed by the caller; 16 words per record: for phase ph < 8 the global
+ * timer in ns at [2 ph] and the SM cycle counter at [2 ph + 1]; record = CTA index of the step kernel, E + env for
+ * the follower kernel).  NULL switches it off.  Not thread-safe; costs one predictable branch per phase when off. */
+void swarm_debug_trace(uint64_t* device_words, int64_t n_words);
+
+/* Destroys the CUDA graphs swarm_step_host caches for the CALLING host thread (one per argument
+ * set, at most 32).  They are also destroyed when the thread exits. */
+void swarm_step_host_clear(void);
 
 /* SwarmStateProcessor.process_state (state_processors.py:25-42): grid + uint8 agent cells.
  * box: nullable (E,4) f64 = [lo_x, hi_x, lo_y, hi_y], i.e. _get_bounding_box (:25-27) of

@@ -1,8 +1,10 @@
-"""Import the *real* reference swarm env / rasteriser by file path (container only).
+"""Import the *real* reference swarm env / rasteriser by file path.
 
 TEST INFRASTRUCTURE.  ``/root/reference`` is mounted read-only in the build
-container and does not exist on the GPU box, so everything that calls
-:func:`load_reference` must be skippable (``reference_available()``).
+container and does not exist on the GPU box; there the byte-identical copies
+staged by ``oracle/make_ref.py`` under ``oracle/_ref/`` (git-ignored, shipped like
+a built .so) are loaded instead.  Everything that calls :func:`load_reference`
+must still be skippable (``reference_available()``).
 
 The reference only needs ``gym.Env`` as a base class whose ``step/reset``
 delegate to ``_step/_reset`` (gym==0.9.4 semantics, requirements.txt:6), so a
@@ -21,7 +23,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SWARM_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = os.environ.get("SWARM_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/fed_gym/envs/multiagent.py") else _STAGED)
 
 _cache = {}
 

@@ -1,0 +1,51 @@
+"""Per-phase timeline of one batch-step (debug facility swarm_debug_trace):  python scripts/trace_step.py 512x256[:ksK][:place] ...
+For every CTA's first env: ns since the kernel's first CTA entered, per phase (median / p90 / max over CTAs)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import golds_rl_gym_b200 as pkg
+M = pkg.submodule("envs.multiagent")
+nat = M.nat
+PLACE = {"follow": 1 << 4, "warps": 2 << 4, "self": 3 << 4}
+PH = ["entry", "loaded", "forces", "stepped", "stored", "raster", "mean", "done"]
+lib = nat.load()
+for s in sys.argv[1:]:
+    parts = s.split(":")
+    E, N = (int(v) for v in parts[0].split("x"))
+    tuning = 0
+    for t in parts[1:]:
+        tuning |= PLACE[t] if t in PLACE else int(t[2:])
+    env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128, tuning=tuning)
+    env.reset()
+    a = torch.randn(E, 10, 2, device="cuda").clamp(-0.7, 0.7).contiguous()
+    for _ in range(6):
+        env.step(a)
+    buf = torch.zeros(2 * E * 16, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    lib.swarm_debug_trace(ctypes.c_void_p(buf.data_ptr()), buf.numel())
+    env.step(a)
+    torch.cuda.synchronize()
+    lib.swarm_debug_trace(None, 0)
+    t = buf.cpu().numpy().reshape(2 * E, 8, 2)
+    gt = t[:, :, 0].astype(np.float64)
+    t0 = gt[gt > 0].min()
+    print("== %s  (globaltimer ns since first entry; SM cycles between consecutive phases of the same record in [])" % s)
+    for name, rows in (("step CTAs", t[:E]), ("follower envs", t[E:])):
+        if not (rows[:, :, 0] > 0).any():
+            continue
+        for ph in range(8):
+            v = rows[:, ph, 0].astype(np.float64)
+            ok = v > 0
+            if not ok.any():
+                continue
+            d = v[ok] - t0
+            line = "  %-13s %-8s n=%5d  med %8.0f  p90 %8.0f  max %8.0f" % (name, PH[ph], ok.sum(), np.median(d), np.percentile(d, 90), d.max())
+            prev = [q for q in range(ph) if (rows[:, q, 0] > 0).any()]
+            if prev:
+                q = prev[-1]
+                both = ok & (rows[:, q, 0] > 0)
+                cyc = (rows[both, ph, 1] - rows[both, q, 1]).astype(np.float64)
+                line += "   [+%6.0f cyc med since %s, max %6.0f]" % (np.median(cyc), PH[q], cyc.max())
+            print(line)
+    del env

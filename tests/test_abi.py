@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_bound(pkg):
         assert hasattr(lib, n), "libswarm_b200.so does not export %s" % n
         assert n in nat.SYMBOLS, "ctypes binding misses %s" % n
     assert sorted(nat.SYMBOLS) == names
-    assert lib.swarm_abi_version() == 2
+    assert lib.swarm_abi_version() == 3
     assert lib.swarm_strerror(0) == b"ok" and b"NULL" in lib.swarm_strerror(-1)
 
 
@@ -54,7 +54,7 @@ def test_ctypes_structs_match_c_layout(pkg, tmp_path):
 
 def _params(nat, **kw):
     base = dict(n_envs=4, n_locusts=80, n_agents=10, grid_size=84, n_burn_in=10, max_episode_steps=128,
-                math_mode=0, reserved=0, noise=1e-4, gravity=-1.0, wind=1.0, F=0.5, L=10.0, dt=0.05,
+                math_mode=0, tuning=0, noise=1e-4, gravity=-1.0, wind=1.0, F=0.5, L=10.0, dt=0.05,
                 box_width=3.0, box_height=3.0, seed=1, env_id_offset=0)
     base.update(kw)
     return nat.SwarmParams(**base)
@@ -107,14 +107,14 @@ def test_torch_extension_loads_and_registers_ops(pkg):
     torch.ops.swarm_b200.*, validates arguments before touching the GPU."""
     import torch
     ops = pkg.load_torch_ops()
-    assert int(ops.abi_version()) == 2
+    assert int(ops.abi_version()) == 3
     for name in ("step", "reset", "rasterize", "expand_obs", "clip_actions", "forces"):
         assert hasattr(ops, name)
     with pytest.raises(RuntimeError):
         ops.clip_actions(torch.zeros(4, 2), 1.0)                       # CPU tensor: refused, no CPU path
     nat = pkg._native
     p = nat.SwarmParams(n_envs=2, n_locusts=8, n_agents=10, grid_size=84, n_burn_in=10, max_episode_steps=128,
-                        math_mode=0, reserved=0, noise=1e-4, gravity=-1.0, wind=1.0, F=0.5, L=10.0, dt=0.05,
+                        math_mode=0, tuning=0, noise=1e-4, gravity=-1.0, wind=1.0, F=0.5, L=10.0, dt=0.05,
                         box_width=3.0, box_height=3.0, seed=0, env_id_offset=0)
     blob = nat.params_blob(p)
     assert blob.dtype == torch.uint8 and blob.numel() == 112

@@ -624,13 +624,16 @@ def test_step_under_cuda_graph_replay_equals_eager(M):
 
 @pytest.mark.parametrize("G", [20, 83, 84])
 def test_follower_rasteriser_large_swarm_grid_sizes(M, G):
-    """N >= 160 takes the two-kernel step (k_step + k_raster_follow on the side stream): observations bit-exact vs
-    the oracle for TMA-able and odd grid sizes, over consecutive steps including an auto-reset, and identical to
-    the in-kernel raster warps (work=None)."""
+    """The two-kernel step (k_step + k_raster_follow on the side stream, forced through SwarmParams.tuning): observations
+    bit-exact vs the oracle for TMA-able and odd grid sizes, over consecutive steps including an auto-reset, and
+    identical to the raster warps inside k_step."""
+    nat = M.nat
     E, N = 37, 176
-    a = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes")
-    b = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes")
-    b.state_c.work = None                                    # static assignment, raster warps inside k_step
+    a = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes",
+                          tuning=1 | nat.TUNE_RASTER_FOLLOW)
+    b = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes",
+                          tuning=1 | nat.TUNE_RASTER_WARPS)
+    b.state_c.work, b.state_c.work_words = None, 0           # static assignment, no work queue
     a.reset(); b.reset()
     rs = np.random.RandomState(G)
     for t in range(5):
@@ -645,3 +648,63 @@ def test_follower_rasteriser_large_swarm_grid_sizes(M, G):
             assert np.array_equal(a.grid[e].cpu().numpy(), g.astype(np.float32)), (G, t, e)
             assert np.array_equal(a.positions[e].cpu().numpy(), p_)
     assert int(a.episode[0]) == 2
+
+
+@pytest.mark.parametrize("N", [40, 64, 128, 176, 256, 320, 512])
+def test_launch_shapes_bitwise_identical(M, N):
+    """swarm_step picks its launch shape by batch size: 1, 2 or 4 warps per 64-locust super-tile (the pair work of a
+    super-tile is cut into four canonical chunks summed in a fixed tree, whoever computes them) and one of three places
+    for the rasteriser (follower kernel, raster warps, the step's own threads).  Every combination must give the same
+    BITS -- a trajectory must not depend on how many envs share a GPU -- and agree with the oracle."""
+    nat = M.nat
+    E = 21
+    ref = None
+    rs = np.random.RandomState(N)
+    acts = [to_dev(clipped(rs, (E, 10, 2))) for _ in range(5)]
+    for ks in (1, 2, 4):
+        for place in (nat.TUNE_RASTER_WARPS, nat.TUNE_RASTER_SELF, nat.TUNE_RASTER_FOLLOW):
+            env = M.BatchedSwarmEnv(E, n_locusts=N, seed=77, max_episode_steps=3, tuning=ks | place)
+            env.reset()
+            v0, r0 = env.forces()
+            outs = [v0.clone(), r0.clone()]
+            for t in range(5):                          # crosses an auto-reset (limit 3) inside the step kernel
+                env.step(acts[t].clone())
+                outs += [env.x.clone(), env.xa.clone(), env.grid.clone(), env.positions.clone(), env.reward.clone(),
+                         env.done_u8.clone(), env.episode.clone(), env.elapsed.clone()]
+            torch.cuda.synchronize()
+            assert int(env.work.sum()) == 0
+            if ref is None:
+                ref = outs
+                x, xa = env.x.cpu().numpy(), env.xa.cpu().numpy()
+                for e in range(0, E, 5):
+                    g, p_ = so.rasterize(x[e], xa[e], 84)
+                    assert np.array_equal(env.grid[e].cpu().numpy(), g.astype(np.float32))
+                    assert np.array_equal(env.positions[e].cpu().numpy(), p_)
+            else:
+                for i, (a, b) in enumerate(zip(ref, outs)):
+                    assert torch.equal(a, b), (N, ks, place >> 4, i)
+
+
+def test_add_wind_false_matches_reference_semantics(M):
+    """SwarmEnv._step(v_action, add_wind=False) (multiagent.py:30,35-36): the action is used as it is, the locusts still
+    feel the wind U.  Checked against the oracle by folding the wind into the action."""
+    N = 80
+    draws = stack_draws([901], N)
+    x, xa = so.reset_injected(*draws)
+    na, nx = draws[3][:, 10], draws[4][:, 10]
+    env = M.BatchedSwarmEnv(1, n_locusts=N, max_episode_steps=0, auto_reset=False, rasterize=False)
+    a = clipped(np.random.RandomState(2), (1, 10, 2)).astype(np.float64)
+    load_state(env, x, xa, na, nx)
+    (gx, gxa), r, _, _ = env.step(to_dev(a), add_wind=False)
+    a_ref = a.copy()
+    a_ref[..., 0] -= 1.0                                  # the oracle always adds WIND_SPEED = 1 (exact in FP64 here?)
+    rew, _ = so.step(x, xa, a_ref, na, nx)
+    # (a - 1) + 1 may differ from a in the last bit: compare the agents to 1e-15 instead of exactly
+    assert np.abs(gxa.cpu().numpy() - xa).max() <= 1e-15
+    assert rel_err(gx.cpu().numpy()[0], x[0]) <= STEP_TOL
+    assert abs(float(r[0]) - rew[0]) <= RTOL * abs(rew[0])
+    # facade: SwarmEnv()._step(a, add_wind=False) no longer raises
+    f = M.SwarmEnv(seed=5)
+    f.reset()
+    st, rr, dd, _ = f._step(np.zeros((10, 2)), add_wind=False)
+    assert rr < 0 and not dd
