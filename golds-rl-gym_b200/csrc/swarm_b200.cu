@@ -55,8 +55,9 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = kp.N, A = kp.A;
     const int n_all = blockDim.x, n_raster = n_all - n_force;
-    const bool raster = n_raster > 0;              // a raster GROUP rides along (kp.raster == 1)
+    const bool raster = kp.raster == 1;            // a raster GROUP rides along
     const bool self_raster = kp.raster == 2;       // the force group rasterises its own env after the step
+    const bool filler = self_raster && kp.filler;  // ... while one extra warp issues / awaits the TMA zero fill
     Smem sm = carve(smem_raw, N, A, kp.G, kp.n_stage, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, kp.raster);
 
     // Env assignment: the first two envs of a CTA are static (blockIdx.x, + gridDim.x); with a work queue the
@@ -72,29 +73,38 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
         if (e < kp.E) prefetch_env(stage_at(smem_raw, N, A, 0), kp, st, io, e, g);
         cp_async_commit();
         const int cells = kp.G * kp.G;
-        const bool tma = self_raster && tma_zero_fill_ok(io.grid, cells);
+        const bool tma = self_raster && !filler && tma_zero_fill_ok(io.grid, cells);
         const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
-        if (self_raster) raster_table_clear(sm, (int)(table_bytes / 4), g);
+        if (self_raster) {
+            raster_table_clear(sm, (int)(table_bytes / 4), g);
+            raster_lut_fill(sm, kp, g.tid, g.n);
+            if (filler) bar_arrive<BAR_FULL>(n_all);       // the table is clean: the filler warp may read its zeros
+        }
         int it = 0;
         if (g.tid == 0) trace_mark(kp, blockIdx.x, TR_ENTRY);
         for (; e < kp.E; ++it) {
-            if (self_raster) {
-                // The observation is ~99 % zeros: they stream out under the whole force phase (TMA bulk stores fed from
-                // the clean counter table, else plain stores); the non-zero cells are scattered over them afterwards.
-                g.sync();                          // the table is clean (first env: just cleared; later: env_raster's exit)
-                float* grid_e = io.grid + (size_t)e * cells * 2;
-                if (tma) {
-                    if (g.tid == 0) tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
-                } else {
-                    raster_zero_fill(grid_e, cells, g.tid, g.n);
-                }
-            }
             int grabbed = 0;                       // the env after next: asked for now, needed an iteration later
             if (dyn && g.tid == 0) grabbed = 2 * (int)gridDim.x + (int)atomicAdd(work, 1u);
             sm.st = stage_at(smem_raw, N, A, it & 1);
             cp_async_wait_all();
             g.sync();      // this env's stage buffer has landed; the other one and sm.nx are free again
             if (it == 0 && g.tid == 0) trace_mark(kp, blockIdx.x, TR_LOADED);
+            if (self_raster && !filler) {
+                // The observation is ~99 % zeros: they stream out under the whole force phase (TMA bulk stores fed from
+                // the clean counter table -- clean and visible since the barrier above --, else plain stores); the
+                // non-zero cells are scattered over them afterwards.  Issued AFTER the env's inputs have landed: a
+                // burst of 56 KB per env from every CTA at once would otherwise sit in front of those loads.  (Normally
+                // the filler warp does this: issuing the bulk stores blocks for microseconds when every CTA does it at once.)
+                float* grid_e = io.grid + (size_t)e * cells * 2;
+                if (tma) {
+                    if (g.tid == g.n - 1) {
+                        tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
+                        if (it == 0) trace_mark(kp, blockIdx.x, TR_ZFILL);
+                    }
+                } else {
+                    raster_zero_fill(grid_e, cells, g.tid, g.n);
+                }
+            }
             if (dyn && it > 0) e1 = sm.mail[1];
             {   // this env's locust noise row: each thread fetches the rows of its own targets, so that its
                 // own wait (before the integration) is all the synchronisation it needs
@@ -181,16 +191,23 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             double2* ox = reinterpret_cast<double2*>(st.x) + (size_t)e * N;
             double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
             double2* rx = sm.rx;
-            for (int i = g.tid; i < N; i += g.n) {
-                const double2 q = sm.st.xs[i];
-                ox[i] = q;
-                if (raster) rx[i] = q;
-            }
-            for (int k = g.tid; k < A; k += g.n) {
-                const double2 q = sm.st.as[k];
-                oa[k] = q;
-                if (raster) rx[N + k] = q;
-            }
+            const Stage stg = sm.st;
+            // the write-back of the new state: by everybody, or -- when this group rasterises its own env -- by the warps
+            // that are not walking the mean, inside env_raster
+            auto write_back = [&](const int tid, const int n) {
+                for (int i = tid; i < N; i += n) {
+                    const double2 q = stg.xs[i];
+                    ox[i] = q;
+                    if (raster) rx[i] = q;
+                }
+                for (int k = tid; k < A; k += n) {
+                    const double2 q = stg.as[k];
+                    oa[k] = q;
+                    if (raster) rx[N + k] = q;
+                }
+            };
+            const bool wb_overlap = self_raster && g.n > 32;
+            if (!wb_overlap) write_back(g.tid, g.n);
             // bar.arrive / bar.sync order the shared-memory writes above for the threads that complete
             // the barrier (PTX ISA, producer/consumer example of barrier.arrive): no extra fence
             if (raster) {
@@ -202,10 +219,21 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                 if (g.tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(work + 2 + e), "r"(1u) : "memory");
             }
             if (it == 0 && g.tid == 0) trace_mark(kp, blockIdx.x, TR_STORED);
-            if (self_raster) {  // state_processors.py:29-42 of the state just written, straight from the stage buffer
-                g.sync();       // [xs | as] of the stage buffer are contiguous = vstack([x, xa])
-                env_raster(sm, sm.st.xs, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma,
-                           NoRelease(), it == 0 ? (long long)blockIdx.x : -1);
+            if (self_raster) {  // state_processors.py:29-42 of the new state, straight from the stage buffer:
+                                // [xs | as] are contiguous = vstack([x, xa]), final and visible since env_step's barrier
+                float* grid_e = io.grid + (size_t)e * cells * 2;
+                uint8_t* pos_e = io.positions + (size_t)e * A * 2;
+                const long long rec = it == 0 ? (long long)blockIdx.x : -1;
+                const ZeroOwn own = {tma, g.n - 1};
+                const ZeroFiller fil = {n_all};
+                if (wb_overlap) {
+                    if (filler) env_raster(sm, stg.xs, kp, g, grid_e, pos_e, true, fil, NoRelease(), write_back, rec);
+                    else env_raster(sm, stg.xs, kp, g, grid_e, pos_e, tma, own, NoRelease(), write_back, rec);
+                } else {
+                    if (filler) env_raster(sm, stg.xs, kp, g, grid_e, pos_e, true, fil, NoRelease(), NoOverlap(), rec);
+                    else env_raster(sm, stg.xs, kp, g, grid_e, pos_e, tma, own, NoRelease(), NoOverlap(), rec);
+                }
+                if (filler && e1 < kp.E) bar_arrive<BAR_FULL>(n_all);   // clean again: the next env's zero fill may start
             }
             e = e1;
             if (!dyn) e1 = e + gridDim.x;
@@ -222,12 +250,33 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                 work[1] = 0u;
             }
         }
-    } else {
+    } else if (filler) {
+        // The filler warp of the SELF shape: streams out the zeros of the CTA's envs (TMA bulk stores fed from the clean
+        // counter table) while the force group computes, and tells it when the table may be written (BAR_ZREAD) and
+        // when the zeros have landed (BAR_ZDONE).
+        const int lane = (int)threadIdx.x - n_force;
+        const int cells = kp.G * kp.G;
+        const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
+        for (int e = blockIdx.x; e < kp.E; e += gridDim.x) {
+            bar_sync<BAR_FULL>(n_all);                     // the force group has (re)cleaned the table
+            if (lane == 0) {
+                tma_zero_fill_issue(io.grid + (size_t)e * cells * 2, sm.table, cells, table_bytes);
+                if (e == (int)blockIdx.x) trace_mark(kp, blockIdx.x, TR_ZFILL);
+                tma_zero_fill_wait_read();
+            }
+            __syncwarp();
+            bar_arrive<BAR_ZREAD>(n_all);
+            if (lane == 0) tma_zero_fill_wait_done();
+            __syncwarp();
+            bar_arrive<BAR_ZDONE>(n_all);
+        }
+    } else if (raster) {
         const RGrp g = {(int)threadIdx.x - n_force, n_raster};
         const int cells = kp.G * kp.G;
         const bool tma = tma_zero_fill_ok(io.grid, cells);
         const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
         raster_table_clear(sm, (int)(table_bytes / 4), g);
+        raster_lut_fill(sm, kp, g.tid, g.n);
         g.sync();
         auto zero_fill = [&](int e) {
             // The observation is ~99 % zeros: stream them out first (TMA bulk stores fed from the clean counter
@@ -250,8 +299,8 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             if (e < 0) break;
             if (!early) zero_fill(e);
             auto release = [n_all]() { bar_arrive<BAR_EMPTY>(n_all); };   // the force group always waits for it
-            env_raster(sm, sm.rx, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma, release,
-                       it == 0 ? (long long)blockIdx.x : -1);
+            env_raster(sm, sm.rx, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma,
+                       ZeroOwn{tma, 0}, release, NoOverlap(), it == 0 ? (long long)blockIdx.x : -1);
         }
     }
 }
@@ -295,6 +344,7 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
     const bool tma = tma_zero_fill_ok(grid, cells);
     const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
     raster_table_clear(sm, (int)(table_bytes / 4), g);
+    raster_lut_fill(sm, kp, g.tid, g.n);
     g.sync();
     double2* pts = sm.rx;
     for (int e = blockIdx.x; e < kp.E; e += gridDim.x) {
@@ -328,7 +378,8 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
         for (int i = g.tid; i < N; i += g.n) pts[i] = __ldcg(gx + i);
         for (int k = g.tid; k < A; k += g.n) pts[N + k] = __ldcg(ga + k);
         g.sync();
-        env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, NoRelease(), (long long)kp.E + e);
+        env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, ZeroOwn{tma, 0}, NoRelease(), NoOverlap(),
+                   (long long)kp.E + e);
         if (g.tid == 0) ready[e] = 0u;          // consumed: the next step's k_step raises it again
     }
 }
@@ -350,8 +401,9 @@ __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __
     for (int k = g.tid; k < kp.A; k += g.n) pts[kp.N + k] = ga[k];
     raster_zero_fill(grid_e, cells, g.tid, g.n);
     raster_table_clear(sm, (int)(smem_table_bytes(kp.N, kp.A, kp.G) / 4), g);
+    raster_lut_fill(sm, kp, g.tid, g.n);
     g.sync();
-    env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, NoRelease());
+    env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, ZeroOwn{false, 0}, NoRelease(), NoOverlap());
     if (box && g.tid == 0) {
         const double m = sm.box[0];
         box[4 * e + 0] = m - kp.half_w;
@@ -552,6 +604,7 @@ KP make_kp(const SwarmParams* p, int mode = 0) {
     k.inv_x = (double)k.G / (2.0 * k.half_w);
     k.inv_P = 1.0 / (double)(k.N + k.A);
     k.inv_G = 1.0 / (double)k.G;
+    k.inv_N = 1.0 / (double)k.N;
     k.trace = g_trace;
     k.trace_slots = g_trace_slots;
     return k;
@@ -757,18 +810,17 @@ bool env_flag(const char* name) {
     return v && v[0] && v[0] != '0';
 }
 
-// Warps per 64-locust super-tile: batches that cannot fill the SMs with one warp per super-tile get 2 or 4, so that the
-// XU pipe still sees ~6+ warps per scheduler (measured on B200: 512 x 256 has 3.5 warps per scheduler at ks = 1 and
-// runs the pair loop at 55 % of the XU rate a full machine reaches).
+// Warps per 64-locust super-tile.  Measured on B200 (profiles/r02_shapes.md): for swarms of 3+ super-tiles the pair loop is
+// XU-pipe-bound on the busiest SMs whatever the warp count (512 x 256: 37.7 us with 1 or 2 warps), so extra warps only
+// cost registers; for one or two super-tiles per env a single-wave batch is latency-bound and two warps per super-tile
+// halve the tile phase (1024 x 64, step's own threads rasterising: 15.9 vs 20.6 us).
 int pick_ks(const SwarmParams* p, int sms) {
     if (!sym64_ok(p->n_locusts)) return 1;
     const int nt2 = (p->n_locusts + 63) / 64;
-    const long long warps = (long long)p->n_envs * nt2;
-    const long long want = (long long)sms * 4 * 6;
-    int ks = 1;
-    while (ks < 4 && warps * ks < want) ks *= 2;
-    while (ks > 1 && ks * nt2 * 32 > kMaxThreads) ks /= 2;
-    return ks;
+    if (nt2 > 2) return 1;
+    const int threads2 = 2 * nt2 * 32 + 32;
+    const long long one_wave2 = (long long)sms * (65536 / (64 * threads2));
+    return p->n_envs <= one_wave2 ? 2 : 1;
 }
 
 }  // namespace
@@ -825,8 +877,23 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
     return check_launch("swarm_reset");
 }
 
-int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const SwarmInjectedDraws* reset_draws,
-               swarm_stream_t stream) {
+}  // extern "C"
+
+namespace {
+
+struct StepPlan {
+    int mode, ks, place;          // force mode (1..6), warps per super-tile, RasterPlace
+    int nf, nt, grid;             // force threads, threads per CTA, CTAs
+    int n_stage, dynamic, raster, filler; // KP fields
+    int follow_threads, rgrid;    // follower launch (place == RASTER_FOLLOW)
+    size_t smem, follow_smem;
+    StepKernel kernel;
+};
+
+// Validates the arguments of swarm_step and decides its launch shape (automatic, or forced through
+// SwarmParams::tuning).  Touches the GPU only for attribute / occupancy queries (cached per device).
+int plan_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const SwarmInjectedDraws* reset_draws,
+              StepPlan* out) {
     int rc = validate(p);
     if (rc) return rc;
     if (!st || !io) return SWARM_ERR_NULL;
@@ -858,7 +925,6 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
         }
         sms = it->second;
     }
-    // ---- launch shape (automatic, or forced through SwarmParams::tuning)
     const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
     if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
     const int mode = force_mode(N, ks);
@@ -897,7 +963,7 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
         // N = 192: 0.123 vs 0.135), the raster warps for small swarms, where the rasteriser -- not the forces -- is the
         // critical path (N = 128: 0.080 vs 0.108 ms, N = 64: 0.052 vs 0.069).  Batches of at most about one wave of
         // one-env CTAs have nothing to hide the rasteriser under: there the step's own threads rasterise (SELF).
-        const int per_sm = 65536 / (64 * nf) > 0 ? 65536 / (64 * nf) : 1;
+        const int per_sm = 65536 / (64 * (nf + 32)) > 0 ? 65536 / (64 * (nf + 32)) : 1;
         if (forced) place = forced;
         else if (E <= (long long)sms * per_sm) place = RASTER_SELF;
         else if (N >= 160) place = RASTER_FOLLOW;
@@ -905,26 +971,68 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
         if (place == RASTER_FOLLOW && !follow_fits) place = RASTER_WARPS;
         if (place == RASTER_WARPS && !warps_fit) place = RASTER_SELF;
     }
-    const bool follow = place == RASTER_FOLLOW, warps = place == RASTER_WARPS, self = place == RASTER_SELF;
-    KP kp = make_kp(p, mode);
-    kp.raster = warps ? 1 : (self ? 2 : 0);
-    kp.n_stage = warps ? 2 : 1;           // one env per CTA (no raster warps): nothing to prefetch into a second buffer
-    kp.wind_step = (io->flags & SWARM_STEP_NO_ACTION_WIND) ? 0 : 1;
-    const size_t smem = step_smem(p, kp.raster, kp.n_stage, mode);
-    if (smem > kMaxSmem) return SWARM_ERR_SIZE;
-    const int nt = nf + (warps ? raster_threads(N, A) : 0);
-    const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;
-    const int has = reset_draws ? 1 : 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = prep(kernel, smem))) return rc;
+    const bool warps = place == RASTER_WARPS, self = place == RASTER_SELF;
+    out->mode = mode; out->ks = ks; out->place = place;
+    out->raster = warps ? 1 : (self ? 2 : 0);
+    out->n_stage = warps ? 2 : 1;         // one env per CTA (no raster warps): nothing to prefetch into a second buffer
+    out->smem = step_smem(p, out->raster, out->n_stage, mode);
+    if (out->smem > kMaxSmem) return SWARM_ERR_SIZE;
+    out->nf = nf;
+    // SELF: one extra warp issues / awaits the TMA zero fill (possible when the grid is a whole number of 16-byte words
+    // per table-sized piece: cells % 8 == 0, 16-byte aligned base)
+    // ... as long as its 32 threads do not push the batch out of a single wave of CTAs (registers)
+    out->filler = (self && ((p->grid_size * p->grid_size) & 7) == 0 && (reinterpret_cast<uintptr_t>(io->grid) & 15) == 0 &&
+                   nf + 32 <= kMaxThreads && E <= (long long)sms * (65536 / (64 * (nf + 32)))) ? 1 : 0;
+    out->nt = nf + (warps ? raster_threads(N, A) : 0) + (out->filler ? 32 : 0);
+    out->kernel = kernel;
+    if ((rc = prep(kernel, out->smem))) return rc;
     int grid = 0;
-    if ((rc = persistent_grid(kernel, nt, smem, E, &grid))) return rc;
+    if ((rc = persistent_grid(kernel, out->nt, out->smem, E, &grid))) return rc;
     // without raster warps to overlap there is nothing to gain from persistence, and hardware-scheduled one-env
     // CTAs measure 8 % faster (C4: 0.154 vs 0.166 ms)
     if (!warps) grid = E;
+    out->grid = grid;
     // the work queue pays off when every CTA has several large envs to work through (one contended atomic per env)
-    kp.dynamic = (warps && have_queue && E >= 3 * grid && (long long)N * (N + A) >= 16384) ? 1 : 0;
-    if (!follow) {
+    out->dynamic = (warps && have_queue && E >= 3 * grid && (long long)N * (N + A) >= 16384) ? 1 : 0;
+    out->follow_threads = follow_threads;
+    out->follow_smem = follow_smem;
+    out->rgrid = rgrid;
+    return SWARM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int swarm_step_plan(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, int32_t out[8]) {
+    if (!out) return SWARM_ERR_NULL;
+    StepPlan pl;
+    const int rc = plan_step(p, st, io, nullptr, &pl);
+    if (rc) return rc;
+    out[0] = pl.mode; out[1] = pl.ks; out[2] = pl.place; out[3] = pl.nt; out[4] = pl.grid;
+    out[5] = (int32_t)pl.smem; out[6] = pl.place == RASTER_FOLLOW ? pl.rgrid : 0;
+    out[7] = pl.place == RASTER_FOLLOW ? 2 : 1;
+    return SWARM_OK;
+}
+
+int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const SwarmInjectedDraws* reset_draws,
+               swarm_stream_t stream) {
+    StepPlan pl;
+    int rc = plan_step(p, st, io, reset_draws, &pl);
+    if (rc) return rc;
+    KP kp = make_kp(p, pl.mode);
+    kp.raster = pl.raster;
+    kp.filler = pl.filler;
+    kp.n_stage = pl.n_stage;
+    kp.dynamic = pl.dynamic;
+    kp.wind_step = (io->flags & SWARM_STEP_NO_ACTION_WIND) ? 0 : 1;
+    const SwarmInjectedDraws dr = reset_draws ? *reset_draws : kNoDraws;
+    const int has = reset_draws ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const StepKernel kernel = pl.kernel;
+    const int grid = pl.grid, nt = pl.nt, nf = pl.nf, rgrid = pl.rgrid, follow_threads = pl.follow_threads;
+    const size_t smem = pl.smem, follow_smem = pl.follow_smem;
+    if (pl.place != RASTER_FOLLOW) {
         kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
         return check_launch("swarm_step");
     }
@@ -973,7 +1081,7 @@ void swarm_step_host_clear(void) { host_cache().clear(); }
 
 void swarm_debug_trace(uint64_t* device_words, int64_t n_words) {
     g_trace = reinterpret_cast<unsigned long long*>(device_words);
-    g_trace_slots = device_words ? n_words / 16 : 0;
+    g_trace_slots = device_words ? n_words / (2 * TR_PHASES) : 0;
 }
 
 int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, const float* host_actions,

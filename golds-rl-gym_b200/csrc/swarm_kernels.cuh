@@ -52,14 +52,15 @@ struct KP {
     int ks;           // MODE 3 family: warps that share one 64-locust super-tile (1, 2 or 4; = the kernel's template KS)
     int raster;       // shared-memory layout of the rasteriser: 0 none, 1 a raster GROUP with its own point buffer, 2 the force
                       // group rasterises its own env after the step (points = the stage buffer)
+    int filler;       // raster == 2: one extra warp per CTA issues the TMA zero fill of the env's grid and waits for it
     int wind_step;    // 0: the step proper does not add the wind to the actions (SwarmEnv._step(add_wind=False))
     unsigned long long* trace;   // debug (swarm_debug_trace): per-CTA phase timestamps, nullptr in production
-    long long trace_slots;       // capacity of trace in 16-word records
+    long long trace_slots;       // capacity of trace in records of 2 * TR_PHASES words
     unsigned char cb[8];   // MODE 3 family: canonical chunk c = segments [cb[c], cb[c+1]) of a warp's pass list (sym64_chunks)
     // rasteriser constants the host can round exactly like numpy does
     double step_y, inv_y; // (2 HEIGHT - 0) / G and its reciprocal
     double inv_x;         // ~ G / WIDTH: only seeds the bin guess (count_le settles ties against the exact edges)
-    double inv_P, inv_G;  // correctly rounded 1/(N+A) and 1/G: exact quotients by one FMA correction (div_by_const)
+    double inv_P, inv_G, inv_N;  // correctly rounded 1/(N+A), 1/G, 1/N: exact quotients by one FMA correction (div_by_const)
 };
 
 // One STAGE buffer = what is prefetched for the step of one env (the locust noise row follows
@@ -85,13 +86,16 @@ struct Smem {
                       //   MODE 2/4: N locusts + A agents
     float2* slot;     // MODE 1/3: nt x nslots x 32 reaction-force partial sums
     float2* own;      // MODE 3 with KS > 1: KS x (nt2 x 64) own-force partial sums of the warps sharing a super-tile
+    float2* agf;      // MODE 1/3: nt x 32 agent pulls, evaluated by the finishing thread BEFORE the tile passes (off the
+                      // critical path after the barrier) and added last
     // ---- rasteriser (present when the kernel rasterises)
     double2* rx;      // N+A: post-step positions handed from the force to the raster group
     int* mail;        // [0] env id handed to the raster group (-1 = no more), [1] next env grabbed from the work queue
     uint32_t* table;  // G*G packed cell counters, 16 bits per cell (two cells per word): locusts in the low
                       // bits, agents above them (kAgentShift); 32 bits per cell (locusts lo16, agents hi16)
                       // when the counts do not fit
-    int* cid;         // N+A: cell written out by this point (or -1)
+    int* cid;         // N+A: cell written out by this point (or -1); before that, the point's y bin count
+    float* lut;       // kLutL + kLutA: grid values count / N (locusts) and count / A (agents) of the small counts
 };
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
@@ -168,14 +172,18 @@ __host__ __device__ inline size_t smem_slot_bytes(int N, int sym) {
 __host__ __device__ inline size_t smem_own_bytes(int N, int sym, int ks) {
     return (sym == 2 && ks > 1) ? smem_align(sizeof(float2) * ks * sym_tiles(N, sym) * 32) : 0;
 }
-__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym, int ks) {
-    return smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) + smem_own_bytes(N, sym, ks);
+__host__ __device__ inline size_t smem_agf_bytes(int N, int sym) {
+    return sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * 32) : 0;
 }
+__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym, int ks) {
+    return smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) + smem_own_bytes(N, sym, ks) + smem_agf_bytes(N, sym);
+}
+constexpr int kLutL = 256, kLutA = 33;     // grid-value look-up: counts below kLutL locusts / kLutA agents per cell
 // raster: 0 none, 1 raster group with its own point buffer, 2 the force group rasterises (points = stage buffer)
 __host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G, int raster) {
     if (!raster) return 0;
     return (raster == 1 ? smem_align(sizeof(double2) * (N + A)) : 0) + smem_table_bytes(N, A, G) +
-           smem_align(sizeof(int) * (N + A));
+           smem_align(sizeof(int) * (N + A)) + smem_align(sizeof(float) * (kLutL + kLutA));
 }
 // n_stage: stage buffers (2 in the pipelined step kernel, 1 in reset/forces, 0 in the rasteriser)
 __host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, int raster, int sym, int ks) {
@@ -207,24 +215,28 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
     s.own = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym));
+    s.agf = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) +
+                                      smem_own_bytes(N, sym, ks));
     if (force) o += smem_force_bytes(N, A, sym, ks);
     s.rx = reinterpret_cast<double2*>(base + o);
     if (raster == 1) o += smem_align(sizeof(double2) * (N + A));
     s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_table_bytes(N, A, G);
-    s.cid = reinterpret_cast<int*>(base + o);
+    s.cid = reinterpret_cast<int*>(base + o);       o += smem_align(sizeof(int) * (N + A));
+    s.lut = reinterpret_cast<float*>(base + o);
     return s;
 }
 
 // ------------------------------------------------------------------------------------------
-// Debug timeline (swarm_debug_trace): record `rec` holds, for phase ph < 8, the global timer (ns) in word 2 ph and the
+// Debug timeline (swarm_debug_trace): record `rec` holds, for phase ph < 16, the global timer (ns) in word 2 ph and the
 // SM's cycle counter in word 2 ph + 1.  One uniform, never-taken branch per call site in production.
-enum : int { TR_ENTRY = 0, TR_LOADED = 1, TR_FORCES = 2, TR_STEPPED = 3, TR_STORED = 4, TR_RASTER = 5, TR_MEAN = 6, TR_DONE = 7 };
+enum : int { TR_ENTRY = 0, TR_ZFILL = 1, TR_LOADED = 2, TR_STAGED = 3, TR_TILES = 4, TR_FORCES = 5, TR_STEPPED = 6, TR_STORED = 7,
+             TR_RASTER = 8, TR_MEAN = 9, TR_BINNED = 10, TR_ZEROS = 11, TR_DONE = 12, TR_PHASES = 16 };
 __device__ __forceinline__ void trace_mark(const KP& kp, const long long rec, const int ph) {
-    if (kp.trace != nullptr && rec < kp.trace_slots) {
+    if (kp.trace != nullptr && rec >= 0 && rec < kp.trace_slots) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        kp.trace[rec * 16 + 2 * ph] = t;
-        kp.trace[rec * 16 + 2 * ph + 1] = (unsigned long long)clock64();
+        kp.trace[rec * 2 * TR_PHASES + 2 * ph] = t;
+        kp.trace[rec * 2 * TR_PHASES + 2 * ph + 1] = (unsigned long long)clock64();
     }
 }
 
@@ -255,7 +267,7 @@ __device__ __forceinline__ void move_particle(double2& p, double2 v, double2 n, 
 }
 
 // Named barriers (bar.sync id, n) of the warp-specialised step kernel.  0 stays __syncthreads.
-enum : int { BAR_FORCE = 1, BAR_RASTER = 2, BAR_FULL = 3, BAR_EMPTY = 4 };
+enum : int { BAR_FORCE = 1, BAR_RASTER = 2, BAR_FULL = 3, BAR_EMPTY = 4, BAR_ZREAD = 5, BAR_ZDONE = 6 };
 
 template <int ID>
 __device__ __forceinline__ void bar_sync(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
@@ -276,6 +288,18 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
+}
+
+// a / b for a divisor whose correctly rounded reciprocal inv_b = RN(1 / b) the host supplies: q0 = RN(a inv_b) is within
+// one ulp, the FMA residual r = a - q0 b is exact and RN(q0 + r inv_b) is the correctly rounded quotient (Markstein
+// 1990) -- three FP64 operations instead of the ~40-instruction division routine.  Outside the range where the
+// residual is exact (quotients near the subnormals / overflow) the plain division is used.
+__device__ __forceinline__ double div_by_const(const double a, const double b, const double inv_b) {
+    const double m = fabs(a);
+    if (!(m > 1e-280 && m < 1e280)) return a / b;
+    const double q0 = __dmul_rn(a, inv_b);
+    const double r = __fma_rn(-q0, b, a);
+    return __fma_rn(r, inv_b, q0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -410,6 +434,13 @@ __device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, c
     const int nfull = (nt - 1) >> 1;
     const float4* S = sm.src;
     const float4 tg = S[I * 64 + lane];
+    {   // the agents' pull on this lane's locust (multiagent.py:108-113), summed from 0 and added last in the finish
+        const float4* ag = S + nt * 64;
+        float gx = 0.f, gy = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
+        sm.agf[I * 32 + lane] = make_float2(gx, gy);
+    }
     ax = 0.f;
     ay = 0.f;
     pair_ordered<PRECISE>(S[I * 64 + lane + 16], tg, kp, ax, ay);
@@ -444,9 +475,9 @@ __device__ __forceinline__ void forces_sym_finish(const Smem& sm, const KP& kp, 
         ax += r.x;
         ay += r.y;
     }
-    const float4 tg = sm.src[I * 64 + lane];
-    const float4* ag = sm.src + nt * 64;        // agents act on locusts only (multiagent.py:108-113)
-    for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, ax, ay);
+    const float2 a = sm.agf[I * 32 + lane];     // written by this very thread in forces_sym_tiles
+    ax += a.x;
+    ay += a.y;
 }
 
 // ---- MODE 3: 64-wide super-tiles, two targets (A: first half, B: second half) per lane -------
@@ -608,6 +639,37 @@ __device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp,
     const int qmax = sym64_qmax(kp.N), seg = sym64_seg(kp.N);
     const float4* S = sm.src;
     const float4 tgA = S[(2 * I) * 64 + lane], tgB = S[(2 * I + 1) * 64 + lane];
+    {   // the agents' pull on the target(s) this thread will FINISH (multiagent.py:108-113), summed from 0 and added
+        // last: evaluated here, where it overlaps with the tile passes, instead of after the barrier
+        const float4* ag = S + nt2 * 128;
+        if constexpr (KS == 1) {
+            float gAx = 0.f, gAy = 0.f, gBx = 0.f, gBy = 0.f;
+            if constexpr (PRECISE) {
+                for (int k = 0; k < kp.A; ++k) {
+                    const float4 q = ag[k];
+                    pair_ordered<PRECISE>(q, tgA, kp, gAx, gAy);
+                    pair_ordered<PRECISE>(q, tgB, kp, gBx, gBy);
+                }
+            } else {
+                const Targets2 t = make_targets2(tgA, tgB);
+                const PairConst2 c = make_pair_const2(kp);
+                f32x2 naA = 0, naB = 0, b = 0;
+#pragma unroll 2
+                for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
+                upk2(naA, gAx, gAy);
+                upk2(naB, gBx, gBy);
+                gAx = -gAx; gAy = -gAy; gBx = -gBx; gBy = -gBy;
+            }
+            sm.agf[(2 * I) * 32 + lane] = make_float2(gAx, gAy);
+            sm.agf[(2 * I + 1) * 32 + lane] = make_float2(gBx, gBy);
+        } else if (cg < 2) {
+            const float4 tg = cg == 0 ? tgA : tgB;
+            float gx = 0.f, gy = 0.f;
+#pragma unroll 2
+            for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
+            sm.agf[(2 * I + cg) * 32 + lane] = make_float2(gx, gy);
+        }
+    }
     constexpr int CH = 4 / KS;                        // canonical chunks run by this thread
     float tAx = 0.f, tAy = 0.f, tBx = 0.f, tBy = 0.f;      // (c0 + c1) [+ (c2 + c3)]
     float uAx = 0.f, uAy = 0.f, uBx = 0.f, uBy = 0.f;      // c_even [+ c_odd]
@@ -691,35 +753,20 @@ __device__ __forceinline__ void sym64_add_reactions(const Smem& sm, const KP& kp
     }
 }
 
-// MODE 3 family, part 2: own partial sums, reactions (fixed order) and the agents' pull.
+// MODE 3 family, part 2: own partial sums, reactions (fixed order) and the agents' pull (sm.agf): v = (own + reactions) + agents.
 // KS = 1: (vx, vy)[2] come in as the own forces of the lane's two targets.  KS > 1: the thread finishes ONE target
 // (target_index), gathers the own partial sums of the KS warps from shared memory; result in (vx, vy)[0].
 template <int KS, bool PRECISE>
 __device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp, const Grp& g, float* vx, float* vy) {
     const int lane = g.tid & 31, W = g.tid >> 5;
     const int nt2 = (kp.N + 63) >> 6;
-    const float4* ag = sm.src + nt2 * 128;      // agents act on locusts only (multiagent.py:108-113)
     if constexpr (KS == 1) {
         const int I = W;
         sym64_add_reactions(sm, kp, 2 * I, lane, vx[0], vy[0]);
         sym64_add_reactions(sm, kp, 2 * I + 1, lane, vx[1], vy[1]);
-        const float4 tgA = sm.src[(2 * I) * 64 + lane], tgB = sm.src[(2 * I + 1) * 64 + lane];
-        if constexpr (PRECISE) {
-            for (int k = 0; k < kp.A; ++k) {
-                const float4 q = ag[k];
-                pair_ordered<PRECISE>(q, tgA, kp, vx[0], vy[0]);
-                pair_ordered<PRECISE>(q, tgB, kp, vx[1], vy[1]);
-            }
-        } else {
-            const Targets2 t = make_targets2(tgA, tgB);
-            const PairConst2 c = make_pair_const2(kp);
-            f32x2 naA = pk2(-vx[0], -vy[0]), naB = pk2(-vx[1], -vy[1]), b = 0;
-#pragma unroll 2
-            for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
-            upk2(naA, vx[0], vy[0]);
-            upk2(naB, vx[1], vy[1]);
-            vx[0] = -vx[0]; vy[0] = -vy[0]; vx[1] = -vx[1]; vy[1] = -vy[1];
-        }
+        const float2 a = sm.agf[(2 * I) * 32 + lane], b = sm.agf[(2 * I + 1) * 32 + lane];   // this thread's own writes
+        vx[0] += a.x; vy[0] += a.y;
+        vx[1] += b.x; vy[1] += b.y;
     } else {
         const int cg = W / nt2, I = W - cg * nt2;
         vx[0] = 0.f;
@@ -734,12 +781,9 @@ __device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp
             y += o2.y + o3.y;
         }
         sym64_add_reactions(sm, kp, H, lane, x, y);
-        const float4 tg = sm.src[H * 64 + lane];
-        // scalar pairs: operation for operation the roundings of pair2_fast (negation is exact)
-#pragma unroll 2
-        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, x, y);
-        vx[0] = x;
-        vy[0] = y;
+        const float2 a = sm.agf[slot];               // this thread's own write
+        vx[0] = x + a.x;
+        vy[0] = y + a.y;
     }
 }
 
@@ -768,19 +812,23 @@ __device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, con
 // contains one group barrier in the unordered-pair modes.
 template <int MODE, bool PRECISE>
 __device__ __forceinline__ void pair_forces(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[ModeT<MODE>::T],
-                                            float (&vy)[ModeT<MODE>::T]) {
+                                            float (&vy)[ModeT<MODE>::T], const long long trace_rec = -1) {
     constexpr int T = ModeT<MODE>::T;
+    if (g.tid == 0) trace_mark(kp, trace_rec, TR_STAGED);
     if constexpr (MODE == 1) {
         forces_sym_tiles<PRECISE>(sm, kp, g, vx[0], vy[0]);
+        if (g.tid == 0) trace_mark(kp, trace_rec, TR_TILES);
         g.sync();
         forces_sym_finish<PRECISE>(sm, kp, g, vx[0], vy[0]);
     } else if constexpr (MODE == 3) {
         forces_sym64_tiles<1, PRECISE>(sm, kp, g, vx, vy);
+        if (g.tid == 0) trace_mark(kp, trace_rec, TR_TILES);
         g.sync();
         forces_sym64_finish<1, PRECISE>(sm, kp, g, vx, vy);
     } else if constexpr (MODE == 5 || MODE == 6) {
         float ax[2], ay[2];
         forces_sym64_tiles<ModeT<MODE>::KS, PRECISE>(sm, kp, g, ax, ay);
+        if (g.tid == 0) trace_mark(kp, trace_rec, TR_TILES);
         g.sync();
         forces_sym64_finish<ModeT<MODE>::KS, PRECISE>(sm, kp, g, vx, vy);
     } else {
@@ -827,7 +875,7 @@ __device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const
     double tot = 0.0;
     const int nw = energy_slots<MODE>(kp, g);
     for (int w = 0; w < nw; ++w) tot += sm.red[w];   // same order in every thread
-    return -tot / (double)kp.N;
+    return -div_by_const(tot, (double)kp.N, kp.inv_N);
 }
 
 // SwarmEnv._step on the stage buffer sm.st.  Preconditions: st.xs/as/an, sm.nx and sm.act filled, each
@@ -851,8 +899,8 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
     stage_locusts<MODE>(sm, kp, g);
     g.sync();
     float vx[T], vy[T];
-    pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy);
-    if (trace_rec >= 0 && g.tid == 0) trace_mark(kp, trace_rec, TR_FORCES);
+    pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy, trace_rec);
+    if (g.tid == 0) trace_mark(kp, trace_rec, TR_FORCES);
     energy_put<MODE>(sm, kp, g, vx, vy);
     cp_async_wait_but_one();   // this thread's own noise rows have landed in sm.nx (no-op outside k_step)
     // multiagent.py:40  locusts move with the pre-cutoff v just computed
@@ -1000,51 +1048,82 @@ __device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA zero fill reads these zeros
 }
 
-// SwarmStateProcessor.process_state (state_processors.py:25-42) of the points pts = [N locusts; A
-// agents] in shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
-// Preconditions: grid_e zero-filled by this group (raster_zero_fill), sm.table all zero and pts
-// visible (a barrier since).  Postcondition: sm.table all zero again, after a group barrier.
-// tma: the zero fill was issued with tma_zero_fill_issue by thread 0 of g (which then also waits).
-// early_release_fn() is called by every thread once it has read its last point from pts (the step
-// kernel hands the buffer back to the force group there).
-struct NoRelease { __device__ __forceinline__ void operator()() const {} };
-
-// a / b for a divisor whose correctly rounded reciprocal inv_b = RN(1 / b) the host supplies: q0 = RN(a inv_b) is within
-// one ulp, the FMA residual r = a - q0 b is exact and RN(q0 + r inv_b) is the correctly rounded quotient (Markstein
-// 1990) -- three FP64 operations instead of the ~40-instruction division routine.  Outside the range where the
-// residual is exact (quotients near the subnormals / overflow) the plain division is used.
-__device__ __forceinline__ double div_by_const(const double a, const double b, const double inv_b) {
-    const double m = fabs(a);
-    if (!(m > 1e-280 && m < 1e280)) return a / b;
-    const double q0 = __dmul_rn(a, inv_b);
-    const double r = __fma_rn(-q0, b, a);
-    return __fma_rn(r, inv_b, q0);
+// grid values of the small counts, once per CTA: lut[c] = c / N (c < kLutL), lut[kLutL + a] = a / A (a < kLutA), rounded
+// like the scatter's own division
+__device__ __forceinline__ void raster_lut_fill(const Smem& sm, const KP& kp, const int tid, const int n) {
+    const float fN = (float)kp.N, fA = (float)(kp.A > 0 ? kp.A : 1);
+    const int nl = kp.N + 1 < kLutL ? kp.N + 1 : kLutL, na = kp.A + 1 < kLutA ? kp.A + 1 : kLutA;
+    for (int c = tid; c < nl; c += n) sm.lut[c] = __fdiv_rn((float)c, fN);
+    for (int c = tid; c < na; c += n) sm.lut[kLutL + c] = __fdiv_rn((float)c, fA);
 }
 
-template <typename Group, typename Release>
+// How env_raster waits for the zero fill of its grid (besides being a group barrier at both points):
+//   ZeroOwn     a thread of the group issued the TMA fill (tma_tid) or the group stored the zeros itself
+//   ZeroFiller  a filler warp outside the group issued it and arrives on BAR_ZREAD / BAR_ZDONE (k_step, SELF shape)
+struct ZeroOwn {
+    bool tma;
+    int tma_tid;
+    template <typename Group>
+    __device__ __forceinline__ void before_table(const Group& g) const {
+        if (tma && g.tid == tma_tid) tma_zero_fill_wait_read();      // the table may be written from here on
+        g.sync();
+    }
+    template <typename Group>
+    __device__ __forceinline__ void before_scatter(const Group& g) const {
+        if (tma && g.tid == tma_tid) tma_zero_fill_wait_done();      // the zeros are in place before anyone scatters over them
+        g.sync();
+    }
+};
+struct ZeroFiller {
+    int n_all;
+    template <typename Group>
+    __device__ __forceinline__ void before_table(const Group&) const { bar_sync<BAR_ZREAD>(n_all); }
+    template <typename Group>
+    __device__ __forceinline__ void before_scatter(const Group&) const { bar_sync<BAR_ZDONE>(n_all); }
+};
+
+// SwarmStateProcessor.process_state (state_processors.py:25-42) of the points pts = [N locusts; A
+// agents] in shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
+// Preconditions: grid_e zero-filled or being zero-filled (see ZeroOwn / ZeroFiller), sm.table all zero, sm.lut filled
+// (raster_lut_fill) and pts visible (a barrier since).  Postcondition: sm.table all zero again, after a group barrier.
+// Phase 0 splits the group: warp 0's first lane walks the sequential mean while the other warps run overlap_fn() (the
+// caller's work that only needs pts, e.g. the write-back of the state) and bin every point's y (the y edges do not
+// depend on the mean) and fill the grid-value table.  early_release_fn() is called by every thread once it has read its
+// last point from pts (the step kernel hands the buffer back to the force group there).
+struct NoRelease { __device__ __forceinline__ void operator()() const {} };
+struct NoOverlap { __device__ __forceinline__ void operator()(int, int) const {} };
+
+template <typename Group, typename Zero, typename Release, typename Overlap>
 __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const Group& g,
                                            float* __restrict__ grid_e, uint8_t* __restrict__ pos_e, const bool tma,
-                                           const Release early_release_fn, const long long trace_rec = -1) {
+                                           const Zero zero, const Release early_release_fn, const Overlap overlap_fn,
+                                           const long long trace_rec = -1) {
     const int N = kp.N, A = kp.A, G = kp.G, P = N + A;
     const bool t16 = table_is16(N, A);
-    if (trace_rec >= 0 && g.tid == 0) trace_mark(kp, trace_rec, TR_RASTER);
-    // phase 0: one thread walks the sequential FP64 mean (np.mean(vstack([x,xa]),axis=0)[0] is a
-    // plain left-to-right sum, one dependent DADD per element)
+    if (g.tid == 0) trace_mark(kp, trace_rec, TR_RASTER);
+    const double lo_y = 0.0, hi_y = kp.y_hi;
+    const double step_y = kp.step_y, inv_y = kp.inv_y;
+    // phase 0
+    const bool split = g.n > 32;
     if (g.tid == 0) {
+        // np.mean(vstack([x,xa]),axis=0)[0] is a plain left-to-right FP64 sum: one dependent DADD per element
         double s = 0.0;
 #pragma unroll 8
         for (int i = 0; i < P; ++i) s = __dadd_rn(s, pts[i].x);
         sm.box[0] = div_by_const(s, (double)P, kp.inv_P);
-        if (trace_rec >= 0) trace_mark(kp, trace_rec, TR_MEAN);
-        if (tma) tma_zero_fill_wait_read();      // the table may be written from here on
+        trace_mark(kp, trace_rec, TR_MEAN);
     }
-    g.sync();
-    // phase 1: bin every point in FP64 against numpy's edges, count with warp-aggregated atomics
+    if (!split || g.tid >= 32) {
+        const int w_tid = split ? g.tid - 32 : g.tid, w_n = split ? g.n - 32 : g.n;
+        if (!split) __syncwarp();
+        overlap_fn(w_tid, w_n);
+        for (int p = w_tid; p < P; p += w_n) sm.cid[p] = count_le(pts[p].y, lo_y, hi_y, step_y, inv_y, G);
+    }
+    zero.before_table(g);
+    // phase 1: bin every point's x in FP64 against numpy's edges, count with warp-aggregated atomics
     const double m = sm.box[0];
     const double lo_x = m - kp.half_w, hi_x = m + kp.half_w;
     const double step_x = div_by_const(hi_x - lo_x, (double)G, kp.inv_G);
-    const double lo_y = 0.0, hi_y = kp.y_hi;
-    const double step_y = kp.step_y;
     // 1 / step_x seeds the bin guess: two Newton steps from the host's G / WIDTH (step_x differs from WIDTH / G by
     // the rounding of mean +- WIDTH/2 only), a real division when the window sits absurdly far out
     double inv_x = kp.inv_x;
@@ -1055,7 +1134,6 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
     } else {
         inv_x = 1.0 / step_x;
     }
-    const double inv_y = kp.inv_y;
     for (int base = 0; base < P; base += g.n) {
         const int p = base + g.tid;
         uint32_t key = 0xffffffffu;
@@ -1064,7 +1142,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
             const bool agent = p >= N;
             const double2 q = pts[p];
             const int cx = count_le(q.x, lo_x, hi_x, step_x, inv_x, G);
-            const int cy = count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
+            const int cy = sm.cid[p];
             if (agent) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
                 pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
                 pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
@@ -1092,8 +1170,9 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
         if (p < P) sm.cid[p] = mine;
     }
     early_release_fn();
-    if (tma && g.tid == 0) tma_zero_fill_wait_done();   // the zeros are in place before anyone scatters over them
-    g.sync();
+    if (g.tid == 0) trace_mark(kp, trace_rec, TR_BINNED);
+    zero.before_scatter(g);
+    if (g.tid == 0) trace_mark(kp, trace_rec, TR_ZEROS);
     // phase 2: sparse scatter of the non-zero cells over the zero fill; the writer cleans its counter
     float2* g2 = reinterpret_cast<float2*>(grid_e);
     for (int p = g.tid; p < P; p += g.n) {
@@ -1111,12 +1190,14 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
                 nl = w & 0xffffu;
                 na = w >> 16;
             }
-            g2[c] = make_float2(__fdiv_rn((float)nl, (float)N), A > 0 ? __fdiv_rn((float)na, (float)A) : 0.f);
+            const float vl = nl < (uint32_t)kLutL ? sm.lut[nl] : __fdiv_rn((float)nl, (float)N);
+            const float va = A > 0 ? (na < (uint32_t)kLutA ? sm.lut[kLutL + na] : __fdiv_rn((float)na, (float)A)) : 0.f;
+            g2[c] = make_float2(vl, va);
         }
     }
     if (tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cleaned counters -> next TMA zero fill
     g.sync();
-    if (trace_rec >= 0 && g.tid == 0) trace_mark(kp, trace_rec, TR_DONE);
+    if (g.tid == 0) trace_mark(kp, trace_rec, TR_DONE);
 }
 
 }  // namespace swarm

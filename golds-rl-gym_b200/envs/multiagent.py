@@ -226,6 +226,23 @@ class BatchedSwarmEnv(object):
             nat.check(rc, "swarm_step")
         return (self.x, self.xa), self.reward, self._done_view, {}
 
+    def plan(self, rasterize=None):
+        """swarm_step_plan: the launch shape step() uses for this batch, as a dict."""
+        io = nat.SwarmStepIO()
+        io.actions_f32 = self.actions.data_ptr()
+        io.reward, io.done = self.reward.data_ptr(), self.done_u8.data_ptr()
+        if self.rasterize if rasterize is None else rasterize:
+            io.grid, io.positions = self._grid_ptr, self._pos_ptr
+        io.flags = nat.SWARM_STEP_AUTO_RESET if self.auto_reset else 0
+        out = (ctypes.c_int32 * 8)()
+        with self._ctx:
+            nat.check(self.lib.swarm_step_plan(self._params_ref, self._state_ref, ctypes.byref(io), out), "swarm_step_plan")
+        keys = ("force_mode", "warps_per_super_tile", "raster_place", "threads", "ctas", "smem_bytes", "follower_ctas",
+                "launches")
+        d = dict(zip(keys, list(out)))
+        d["raster_place"] = ("none", "follower kernel", "raster warps in k_step", "k_step's own threads")[d["raster_place"]]
+        return d
+
     # ------------------------------------------------------------------ host-buffer (end-to-end) form
     def step_host(self, host_actions, host_reward, host_done, host_grid=None, host_positions=None):
         """swarm_step_host: actions come from / reward+done go to HOST tensors; the observation stays in HBM

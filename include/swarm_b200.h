@@ -150,6 +150,11 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
 int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
                const SwarmInjectedDraws* reset_draws, swarm_stream_t stream);
 
+/* The launch shape swarm_step would use for these arguments (no launch; needs the device for occupancy queries):
+ * out = { force mode, warps per 64-locust super-tile, rasteriser placement (0 none, 1 follower kernel, 2 raster warps,
+ * 3 the step's own threads), threads per CTA, CTAs, dynamic shared memory bytes, follower CTAs, kernel launches }. */
+int swarm_step_plan(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, int32_t out[8]);
+
 /* Same call with HOST buffers for the per-step inputs/results; synchronises the stream before
  * returning.  With PINNED host buffers (cudaHostAlloc / torch pin_memory: device-visible under
  * UVA) the kernel reads host_actions and writes host_reward / host_done directly over PCIe --
@@ -164,9 +169,9 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
                     float* host_grid, uint8_t* host_positions, swarm_stream_t stream);
 
 /* Debug only: from now on every step / rasteriser kernel of this process records phase timestamps of each CTA's first
- * env into device_words (n_words uint64, zeroed by the caller; 16 words per record: for phase ph < 8 the global
+ * env into device_words (n_words uint64, zeroed by the caller; 32 words per record: for phase ph < 16 the global
  * timer in ns at [2 ph] and the SM cycle counter at [2 ph + 1]; record = CTA index of the step kernel, E + env for
- * the follower kernel).  NULL switches it off.  Not thread-safe; costs one predictable branch per phase when off. */
+ * the follower kernel; phases: see scripts/trace_step.py).  NULL switches it off.  Not thread-safe; costs one predictable branch per phase when off. */
 void swarm_debug_trace(uint64_t* device_words, int64_t n_words);
 
 /* Destroys the CUDA graphs swarm_step_host caches for the CALLING host thread (one per argument

@@ -42,6 +42,8 @@ def timed(fn, k):
 
 
 def run(E, N, boundary, reps=5, **kw):
+    if not kw.get("tuning"):
+        kw.pop("tuning", None)          # (the round-1 tree under .r1_baseline has no such argument)
     env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128, **kw)
     env.reset()
     acts = []

@@ -8,7 +8,8 @@ import golds_rl_gym_b200 as pkg
 M = pkg.submodule("envs.multiagent")
 nat = M.nat
 PLACE = {"follow": 1 << 4, "warps": 2 << 4, "self": 3 << 4}
-PH = ["entry", "loaded", "forces", "stepped", "stored", "raster", "mean", "done"]
+PH = ["entry", "zfill", "loaded", "staged", "tiles", "forces", "stepped", "stored", "raster", "mean", "binned", "zeros", "done",
+      "-", "-", "-"]
 lib = nat.load()
 for s in sys.argv[1:]:
     parts = s.split(":")
@@ -18,23 +19,24 @@ for s in sys.argv[1:]:
         tuning |= PLACE[t] if t in PLACE else int(t[2:])
     env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128, tuning=tuning)
     env.reset()
+    print("plan", env.plan())
     a = torch.randn(E, 10, 2, device="cuda").clamp(-0.7, 0.7).contiguous()
     for _ in range(6):
         env.step(a)
-    buf = torch.zeros(2 * E * 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(2 * E * 32, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     lib.swarm_debug_trace(ctypes.c_void_p(buf.data_ptr()), buf.numel())
     env.step(a)
     torch.cuda.synchronize()
     lib.swarm_debug_trace(None, 0)
-    t = buf.cpu().numpy().reshape(2 * E, 8, 2)
+    t = buf.cpu().numpy().reshape(2 * E, 16, 2)
     gt = t[:, :, 0].astype(np.float64)
     t0 = gt[gt > 0].min()
     print("== %s  (globaltimer ns since first entry; SM cycles between consecutive phases of the same record in [])" % s)
     for name, rows in (("step CTAs", t[:E]), ("follower envs", t[E:])):
         if not (rows[:, :, 0] > 0).any():
             continue
-        for ph in range(8):
+        for ph in range(16):
             v = rows[:, ph, 0].astype(np.float64)
             ok = v > 0
             if not ok.any():
