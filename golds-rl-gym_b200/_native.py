@@ -14,6 +14,8 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 _REPO = os.path.dirname(_PKG_DIR)
 LIB_PATH = os.path.join(_PKG_DIR, "libswarm_b200.so")
+# experiments only (scripts/build_variants.py): load another build of the same ABI through the ctypes binding
+_LIB_OVERRIDE = os.environ.get("SWARM_B200_LIB")
 SOURCES = [os.path.join(_CSRC, f) for f in ("swarm_b200.cu", "swarm_kernels.cuh", "swarm_philox.cuh")]
 HEADER = os.path.join(_REPO, "include", "swarm_b200.h")
 
@@ -30,7 +32,7 @@ SWARM_STEP_CLIP_ACTIONS = 2
 SWARM_STEP_ACTIONS_F64 = 4
 SWARM_STEP_NO_ACTION_WIND = 8
 SWARM_STEP_INKERNEL_RASTER = 16
-# SwarmParams.tuning: bits 0-2 warps per 64-locust super-tile (0 auto / 1 / 2 / 4), bits 4-5 rasteriser placement
+# SwarmParams.tuning: bits 4-5 = rasteriser placement (0 automatic); every other bit must be 0
 TUNE_RASTER_FOLLOW, TUNE_RASTER_WARPS, TUNE_RASTER_SELF = 1 << 4, 2 << 4, 3 << 4
 
 
@@ -158,9 +160,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if needs_build():
-        build()                         # raises SwarmNativeError: no compiler, or the compile failed
-    lib = ctypes.CDLL(LIB_PATH)
+    if _LIB_OVERRIDE:
+        lib = ctypes.CDLL(_LIB_OVERRIDE)
+    else:
+        if needs_build():
+            build()                     # raises SwarmNativeError: no compiler, or the compile failed
+        lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)           # AttributeError if the symbol is not exported
         fn.restype = res

@@ -51,13 +51,14 @@ class GridPAACLearner(object):
         # same function of the observation, without ever materialising the reference's (E,A,G,G,3) layout
         self._compact_request = compact_obs
         torch.backends.cudnn.benchmark = True       # fixed shapes: let cuDNN pick its fastest algorithms once
-        # net_precision: "fp32" = PyTorch defaults (FP32 dense layers, cuDNN convolutions may use TF32), "tf32" also lets
-        # the dense layers use TF32 tensor cores, "bf16" runs forward/backward under autocast (FP32 master weights).
+        # net_precision: "fp32" = true FP32 like the reference's TF graph (networks.py:165-167): TF32 is switched OFF for
+        # cuDNN convolutions and cuBLAS matmuls (PyTorch leaves it on for convolutions by default); "tf32" lets both use
+        # TF32 tensor cores; "bf16" runs forward/backward under autocast (FP32 master weights).  Process-wide switches.
         if net_precision not in ("fp32", "tf32", "bf16"):
             raise ValueError("net_precision must be fp32, tf32 or bf16")
         self.net_precision = net_precision
-        if net_precision == "tf32":
-            torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = net_precision != "fp32"
+        torch.backends.cuda.matmul.allow_tf32 = net_precision != "fp32"
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -275,11 +276,27 @@ class GridPAACLearner(object):
         else:
             self._update_body()
 
-    def train(self, max_updates=None, log_every=None, monitor=None, eval_every=30.0):
+    def scalars(self):
+        """The training scalars the reference writes as TF summaries: ``global_norm`` (actor_learner.py:83) and
+        ``rl/reward`` = mean total reward of the episodes finished so far (paac.py:152-155, 384-395), plus the step
+        count and learning rate.  One device->host read: call it when logging, not every update."""
+        n = int(self.finished_episodes.item())
+        return {"global_step": int(self.global_step), "global_norm": float(self.global_norm.item()),
+                "rl/reward": float(self.finished_return_sum.item()) / n if n else 0.0, "rl/episodes": n,
+                "learning_rate": float(self.get_lr())}
+
+    def train(self, max_updates=None, log_every=None, monitor=None, eval_every=30.0, summary_dir=None):
         """paac.py:226-406 without the TF session.  ``monitor``: a SwarmPolicyMonitor evaluated every
         ``eval_every`` seconds (the reference does this from a thread, paac.py:277-282; here between updates,
-        on rank 0).  Returns the mean frames/s."""
+        on rank 0).  ``summary_dir``: where rank 0 appends scalars() as JSON lines (``summaries.jsonl``) at every
+        log point -- the stand-in for the reference's TF summary writer.  Returns the mean frames/s."""
+        import json
+        import os
         self.start()
+        summary_f = None
+        if summary_dir is not None and self.rank == 0:
+            os.makedirs(summary_dir, exist_ok=True)
+            summary_f = open(os.path.join(summary_dir, "summaries.jsonl"), "a")
         counter, start = 0, time.time()
         log_every = log_every or max(1, int(5048 / self.total_emulators))
         global_step_start = self.global_step
@@ -295,14 +312,20 @@ class GridPAACLearner(object):
             if counter % log_every == 0 and self.rank == 0:
                 torch.cuda.synchronize(self.device)
                 now = time.time()
-                n = int(self.finished_episodes.item())
-                avg = float(self.finished_return_sum.item()) / n if n else 0.0
+                sc = self.scalars()
+                avg = sc["rl/reward"]
+                if summary_f is not None:
+                    summary_f.write(json.dumps(sc) + "\n")
+                    summary_f.flush()
                 logging.info("Ran %d steps, at %.1f steps/s (%.1f steps/s avg), mean finished-episode reward %.3f, "
                              "grad norm %.3f", self.global_step,
                              log_every * self.max_local_steps * self.total_emulators / (now - loop_start),
                              (self.global_step - global_step_start) / (now - start), avg, float(self.global_norm.item()))
                 loop_start = now
         torch.cuda.synchronize(self.device)
+        if summary_f is not None:
+            summary_f.write(json.dumps(self.scalars()) + "\n")
+            summary_f.close()
         return (self.global_step - global_step_start) / max(time.time() - start, 1e-9)
 
     def cleanup(self):

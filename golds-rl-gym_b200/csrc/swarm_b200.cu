@@ -49,37 +49,39 @@ __device__ __forceinline__ void prefetch_env(const Stage& sg, const KP& kp, cons
 // so that the rasteriser of env e (latency chains + 56 KB of stores) and the HBM reads of env
 // e + gridDim.x both run under a force phase.  Hand-over: named barriers FULL[b] (force arrives,
 // raster waits) and EMPTY[b] (raster arrives, force waits before re-using rx[b] two envs later).
-template <int MODE, bool PRECISE>
+// PLACE (compile time, so that every instantiation only carries the code it runs -- the kernel is instruction-cache
+// sensitive): 0 no rasteriser in this kernel (none wanted, or k_raster_follow trails it), 2 a raster GROUP rides along,
+// 3 the force group rasterises its own env after the step (SELF; optionally with a filler warp for the TMA zero fill).
+template <int MODE, bool PRECISE, int PLACE>
 __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const SwarmStepIO io,
                                        const SwarmInjectedDraws dr, const int has_draws, const int n_force) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = kp.N, A = kp.A;
     const int n_all = blockDim.x, n_raster = n_all - n_force;
-    const bool raster = kp.raster == 1;            // a raster GROUP rides along
-    const bool self_raster = kp.raster == 2;       // the force group rasterises its own env after the step
+    constexpr bool raster = PLACE == 2;            // a raster GROUP rides along
+    constexpr bool self_raster = PLACE == 3;       // the force group rasterises its own env after the step
     const bool filler = self_raster && kp.filler;  // ... while one extra warp issues / awaits the TMA zero fill
-    Smem sm = carve(smem_raw, N, A, kp.G, kp.n_stage, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, kp.raster);
+    Smem sm = carve(smem_raw, N, A, kp.G, kp.n_stage, true, ModeT<MODE>::SYM, raster ? 1 : (self_raster ? 2 : 0));
 
     // Env assignment: the first two envs of a CTA are static (blockIdx.x, + gridDim.x); with a work queue the
     // later ones are drawn from an atomic counter (index 2 * gridDim.x + ticket), which evens out the CTAs'
     // finishing times; without, the static stride continues.
     uint32_t* const work = st.work;
-    const bool dyn = kp.dynamic != 0;
+    const bool dyn = raster && kp.dynamic != 0;
 
     if ((int)threadIdx.x < n_force) {
         const Grp g = {(int)threadIdx.x, n_force};
         constexpr int T = ModeT<MODE>::T;
         int e = blockIdx.x, e1 = blockIdx.x + gridDim.x;   // the env of this iteration and of the next one
-        if (e < kp.E) prefetch_env(stage_at(smem_raw, N, A, 0), kp, st, io, e, g);
-        cp_async_commit();
         const int cells = kp.G * kp.G;
-        const bool tma = self_raster && !filler && tma_zero_fill_ok(io.grid, cells);
-        const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
-        if (self_raster) {
-            raster_table_clear(sm, (int)(table_bytes / 4), g);
+        if constexpr (self_raster) {       // shared-memory prologue: independent of the previous kernel's results
+            raster_table_clear(sm, (int)(smem_table_bytes(N, A, kp.G) / 4), g);
             raster_lut_fill(sm, kp, g.tid, g.n);
             if (filler) bar_arrive<BAR_FULL>(n_all);       // the table is clean: the filler warp may read its zeros
         }
+        pdl_wait();                        // from here on the previous kernels' writes (state, actions, grid) are visible
+        if (e < kp.E) prefetch_env(stage_at(smem_raw, N, A, 0), kp, st, io, e, g);
+        cp_async_commit();
         int it = 0;
         if (g.tid == 0) trace_mark(kp, blockIdx.x, TR_ENTRY);
         for (; e < kp.E; ++it) {
@@ -89,21 +91,13 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             cp_async_wait_all();
             g.sync();      // this env's stage buffer has landed; the other one and sm.nx are free again
             if (it == 0 && g.tid == 0) trace_mark(kp, blockIdx.x, TR_LOADED);
-            if (self_raster && !filler) {
-                // The observation is ~99 % zeros: they stream out under the whole force phase (TMA bulk stores fed from
-                // the clean counter table -- clean and visible since the barrier above --, else plain stores); the
-                // non-zero cells are scattered over them afterwards.  Issued AFTER the env's inputs have landed: a
-                // burst of 56 KB per env from every CTA at once would otherwise sit in front of those loads.  (Normally
-                // the filler warp does this: issuing the bulk stores blocks for microseconds when every CTA does it at once.)
-                float* grid_e = io.grid + (size_t)e * cells * 2;
-                if (tma) {
-                    if (g.tid == g.n - 1) {
-                        tma_zero_fill_issue(grid_e, sm.table, cells, table_bytes);
-                        if (it == 0) trace_mark(kp, blockIdx.x, TR_ZFILL);
-                    }
-                } else {
-                    raster_zero_fill(grid_e, cells, g.tid, g.n);
-                }
+            if (it == 0) pdl_launch_dependents();       // the next kernel's CTAs may take free SM slots from now on
+            if constexpr (self_raster) {
+                // Without a filler warp (odd grid sizes, or no room for its 32 threads) the group streams the env's zeros
+                // out itself with plain stores -- AFTER the env's inputs have landed: a burst of 56 KB per env from every
+                // CTA at once would otherwise sit in front of those loads.  (Issuing TMA bulk stores from a force thread was
+                // measured and dropped: the issue blocks for microseconds when every CTA does it at once.)
+                if (!filler) raster_zero_fill(io.grid + (size_t)e * cells * 2, cells, g.tid, g.n);
             }
             if (dyn && it > 0) e1 = sm.mail[1];
             {   // this env's locust noise row: each thread fetches the rows of its own targets, so that its
@@ -160,7 +154,7 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             for (;;) {
                 // multiagent.py:30,35-36: _step(add_wind=False) leaves the action alone; the burn-in steps of a reset
                 // always go through step() with the default add_wind=True (multiagent.py:59-61)
-                const double reward = env_step<MODE, PRECISE>(sm, kp, g, v_out, (r < 0 && !kp.wind_step) ? 0.0 : kp.wind,
+                const double reward = env_step<MODE, PRECISE, self_raster>(sm, kp, g, v_out, (r < 0 && !kp.wind_step) ? 0.0 : kp.wind,
                                                               (r < 0 && it == 0) ? (long long)blockIdx.x : -1);
                 if (r < 0) {
                     // multiagent.py:44 done = reward >= 0; gym TimeLimit: done |= ++elapsed >= max_episode_steps
@@ -192,8 +186,8 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
             double2* rx = sm.rx;
             const Stage stg = sm.st;
-            // the write-back of the new state: by everybody, or -- when this group rasterises its own env -- by the warps
-            // that are not walking the mean, inside env_raster
+            // the write-back of the new state: by everybody, or -- when this group rasterises its own env -- inside
+            // env_raster by the warps that are not walking the mean
             auto write_back = [&](const int tid, const int n) {
                 for (int i = tid; i < N; i += n) {
                     const double2 q = stg.xs[i];
@@ -206,39 +200,29 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                     if (raster) rx[N + k] = q;
                 }
             };
-            const bool wb_overlap = self_raster && g.n > 32;
-            if (!wb_overlap) write_back(g.tid, g.n);
+            if constexpr (!self_raster) write_back(g.tid, g.n);
             // bar.arrive / bar.sync order the shared-memory writes above for the threads that complete
             // the barrier (PTX ISA, producer/consumer example of barrier.arrive): no extra fence
-            if (raster) {
+            if constexpr (raster) {
                 if (g.tid == 0) sm.mail[0] = e;
                 bar_arrive<BAR_FULL>(n_all);
             }
-            if (kp.publish) {   // tell the concurrently running k_raster_follow that env e's new state is in memory
+            if (PLACE == 0 && kp.publish) {   // tell the concurrently running k_raster_follow that env e's new state is in memory
                 g.sync();
                 if (g.tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(work + 2 + e), "r"(1u) : "memory");
             }
             if (it == 0 && g.tid == 0) trace_mark(kp, blockIdx.x, TR_STORED);
-            if (self_raster) {  // state_processors.py:29-42 of the new state, straight from the stage buffer:
-                                // [xs | as] are contiguous = vstack([x, xa]), final and visible since env_step's barrier
-                float* grid_e = io.grid + (size_t)e * cells * 2;
-                uint8_t* pos_e = io.positions + (size_t)e * A * 2;
-                const long long rec = it == 0 ? (long long)blockIdx.x : -1;
-                const ZeroOwn own = {tma, g.n - 1};
-                const ZeroFiller fil = {n_all};
-                if (wb_overlap) {
-                    if (filler) env_raster(sm, stg.xs, kp, g, grid_e, pos_e, true, fil, NoRelease(), write_back, rec);
-                    else env_raster(sm, stg.xs, kp, g, grid_e, pos_e, tma, own, NoRelease(), write_back, rec);
-                } else {
-                    if (filler) env_raster(sm, stg.xs, kp, g, grid_e, pos_e, true, fil, NoRelease(), NoOverlap(), rec);
-                    else env_raster(sm, stg.xs, kp, g, grid_e, pos_e, tma, own, NoRelease(), NoOverlap(), rec);
-                }
+            if constexpr (self_raster) {
+                // state_processors.py:29-42 of the new state, straight from the stage buffer: [xs | as] are contiguous
+                // = vstack([x, xa]), final and visible since env_step's closing barrier
+                env_raster<true>(sm, stg.xs, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, filler,
+                                 ZeroSelf{filler, n_all}, NoRelease(), write_back, it == 0 ? (long long)blockIdx.x : -1);
                 if (filler && e1 < kp.E) bar_arrive<BAR_FULL>(n_all);   // clean again: the next env's zero fill may start
             }
             e = e1;
             if (!dyn) e1 = e + gridDim.x;
         }
-        if (raster) {      // tell the raster group that nothing more is coming
+        if constexpr (raster) {      // tell the raster group that nothing more is coming
             if (it >= 1) bar_sync<BAR_EMPTY>(n_all);
             if (g.tid == 0) sm.mail[0] = -1;
             bar_arrive<BAR_FULL>(n_all);
@@ -250,13 +234,15 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
                 work[1] = 0u;
             }
         }
-    } else if (filler) {
+    } else if constexpr (self_raster) {
         // The filler warp of the SELF shape: streams out the zeros of the CTA's envs (TMA bulk stores fed from the clean
         // counter table) while the force group computes, and tells it when the table may be written (BAR_ZREAD) and
         // when the zeros have landed (BAR_ZDONE).
         const int lane = (int)threadIdx.x - n_force;
         const int cells = kp.G * kp.G;
         const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
+        pdl_wait();                                        // the grid may still be read / written by the previous kernels
+        pdl_launch_dependents();
         for (int e = blockIdx.x; e < kp.E; e += gridDim.x) {
             bar_sync<BAR_FULL>(n_all);                     // the force group has (re)cleaned the table
             if (lane == 0) {
@@ -270,7 +256,7 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             __syncwarp();
             bar_arrive<BAR_ZDONE>(n_all);
         }
-    } else if (raster) {
+    } else if constexpr (raster) {
         const RGrp g = {(int)threadIdx.x - n_force, n_raster};
         const int cells = kp.G * kp.G;
         const bool tma = tma_zero_fill_ok(io.grid, cells);
@@ -278,6 +264,8 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
         raster_table_clear(sm, (int)(table_bytes / 4), g);
         raster_lut_fill(sm, kp, g.tid, g.n);
         g.sync();
+        pdl_wait();                                        // the grid may still be read / written by the previous kernels
+        pdl_launch_dependents();
         auto zero_fill = [&](int e) {
             // The observation is ~99 % zeros: stream them out first (TMA bulk stores fed from the clean counter
             // table, else plain stores); the non-zero cells are scattered over them afterwards.
@@ -299,8 +287,8 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             if (e < 0) break;
             if (!early) zero_fill(e);
             auto release = [n_all]() { bar_arrive<BAR_EMPTY>(n_all); };   // the force group always waits for it
-            env_raster(sm, sm.rx, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma,
-                       ZeroOwn{tma, 0}, release, NoOverlap(), it == 0 ? (long long)blockIdx.x : -1);
+            env_raster<false>(sm, sm.rx, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, tma,
+                              ZeroOwn{tma, 0}, release, NoOverlap(), it == 0 ? (long long)blockIdx.x : -1);
         }
     }
 }
@@ -312,7 +300,7 @@ __global__ void __maxnreg__(64) k_reset(const KP kp, const SwarmState st, const 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     if (mask && !mask[e]) return;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, 0);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM, 0);
     const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const uint32_t ep = st.episode[e];
     const ResetCtx rc = reset_begin(sm, kp, g, e, ep, has_draws != 0, dr);
@@ -339,7 +327,7 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
                                                        uint8_t* __restrict__ positions, uint32_t* ready) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = kp.N, A = kp.A, cells = kp.G * kp.G;
-    const Smem sm = carve(smem_raw, N, A, kp.G, 0, false, 0, 1, 1);
+    const Smem sm = carve(smem_raw, N, A, kp.G, 0, false, 0, 1);
     const RGrp g = {(int)threadIdx.x, (int)blockDim.x};
     const bool tma = tma_zero_fill_ok(grid, cells);
     const uint32_t table_bytes = (uint32_t)smem_table_bytes(N, A, kp.G);
@@ -378,8 +366,8 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
         for (int i = g.tid; i < N; i += g.n) pts[i] = __ldcg(gx + i);
         for (int k = g.tid; k < A; k += g.n) pts[N + k] = __ldcg(ga + k);
         g.sync();
-        env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, ZeroOwn{tma, 0}, NoRelease(), NoOverlap(),
-                   (long long)kp.E + e);
+        env_raster<false>(sm, pts, kp, g, grid_e, positions + (size_t)e * A * 2, tma, ZeroOwn{tma, 0}, NoRelease(), NoOverlap(),
+                          (long long)kp.E + e);
         if (g.tid == 0) ready[e] = 0u;          // consumed: the next step's k_step raises it again
     }
 }
@@ -391,7 +379,7 @@ __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     const int cells = kp.G * kp.G;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 0, false, 0, 1, 1);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 0, false, 0, 1);
     const RGrp g = {(int)threadIdx.x, (int)blockDim.x};
     float* grid_e = grid + (size_t)e * cells * 2;
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
@@ -403,7 +391,7 @@ __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __
     raster_table_clear(sm, (int)(smem_table_bytes(kp.N, kp.A, kp.G) / 4), g);
     raster_lut_fill(sm, kp, g.tid, g.n);
     g.sync();
-    env_raster(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, ZeroOwn{false, 0}, NoRelease(), NoOverlap());
+    env_raster<false>(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, ZeroOwn{false, 0}, NoRelease(), NoOverlap());
     if (box && g.tid == 0) {
         const double m = sm.box[0];
         box[4 * e + 0] = m - kp.half_w;
@@ -421,7 +409,7 @@ __global__ void __maxnreg__(64) k_forces(const KP kp, const double* __restrict__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int e = blockIdx.x;
     constexpr int T = ModeT<MODE>::T;
-    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM, ModeT<MODE>::KS, 0);
+    const Smem sm = carve(smem_raw, kp.N, kp.A, kp.G, 1, true, ModeT<MODE>::SYM, 0);
     const Grp g = {(int)threadIdx.x, (int)blockDim.x};
     const double2* gx = reinterpret_cast<const double2*>(x) + (size_t)e * kp.N;
     const double2* ga = reinterpret_cast<const double2*>(xa) + (size_t)e * kp.A;
@@ -535,21 +523,18 @@ constexpr size_t kMaxSmem = 227 * 1024;
 constexpr int kMaxLocusts = 2048;
 constexpr int kMaxThreads = 1024;
 
-// N <= 512: unordered pairs -- the MODE 3 family (64-wide super-tiles, two targets per lane; ks = 1, 2 or 4 warps per
-// super-tile -> MODE 3, 5, 6) when N pads to a multiple of 64 anyway, else MODE 1 (32-wide tiles, one target per
-// lane); N > 512: ordered pairs with 2 or 4 targets per thread (MODE 2/4).
-bool sym64_ok(int N) { return N <= kSymMaxLocusts && ((N + 63) / 64) * 64 == ((N + 31) / 32) * 32; }
-int force_mode(int N, int ks = 1) {
-    if (sym64_ok(N)) return ks >= 4 ? 6 : (ks == 2 ? 5 : 3);
-    if (N <= kSymMaxLocusts) return 1;
+// N <= 512: unordered pairs -- MODE 3 (64-wide super-tiles, two targets per lane) when N pads to a
+// multiple of 64 anyway, else MODE 1 (32-wide tiles, one target per lane); N > 512: ordered pairs
+// with 2 or 4 targets per thread (MODE 2/4).
+int force_mode(int N) {
+    if (N <= kSymMaxLocusts) return ((N + 63) / 64) * 64 == ((N + 31) / 32) * 32 ? 3 : 1;
     return N <= 1024 ? 2 : 4;
 }
-int force_sym(int mode) { return mode == 1 ? 1 : ((mode == 3 || mode == 5 || mode == 6) ? 2 : 0); }
-int mode_ks(int mode) { return mode == 5 ? 2 : (mode == 6 ? 4 : 1); }
+int force_sym(int mode) { return mode == 1 ? 1 : (mode == 3 ? 2 : 0); }
 
 // threads of the force group
 int block_threads(int N, int mode) {
-    if (force_sym(mode) == 2) return mode_ks(mode) * ((N + 63) / 64) * 32;
+    if (mode == 3) return ((N + 63) / 64) * 32;
     const int per = (N + mode - 1) / mode;
     return ((per + 31) / 32) * 32;
 }
@@ -560,7 +545,7 @@ int raster_threads(int N, int A) { return (N + A) <= 1024 ? 64 : 128; }
 
 // raster: 0 none, 1 raster group (own point buffer), 2 the force group rasterises
 size_t step_smem(const SwarmParams* p, int raster, int n_stage, int mode) {
-    return smem_bytes(p->n_locusts, p->n_agents, p->grid_size, n_stage, true, raster, force_sym(mode), mode_ks(mode));
+    return smem_bytes(p->n_locusts, p->n_agents, p->grid_size, n_stage, true, raster, force_sym(mode));
 }
 
 int validate(const SwarmParams* p, int min_agents = 1) {
@@ -570,7 +555,7 @@ int validate(const SwarmParams* p, int min_agents = 1) {
     if (p->grid_size < 2 || p->grid_size > 255) return SWARM_ERR_SIZE;      // positions are uint8
     if (p->n_burn_in < 0 || p->max_episode_steps < 0) return SWARM_ERR_SIZE;
     if (p->math_mode != 0 && p->math_mode != 1) return SWARM_ERR_FLAGS;
-    if (p->tuning < 0 || p->tuning > 0x3f) return SWARM_ERR_FLAGS;
+    if (p->tuning < 0 || (p->tuning & ~0x30)) return SWARM_ERR_FLAGS;
     if (step_smem(p, 1, 2, force_mode(p->n_locusts)) > kMaxSmem) return SWARM_ERR_SIZE;
     if (p->env_id_offset < 0 || p->env_id_offset + p->n_envs > (int64_t)0xffffffffLL) return SWARM_ERR_SIZE;
     return SWARM_OK;
@@ -594,10 +579,8 @@ KP make_kp(const SwarmParams* p, int mode = 0) {
     k.dynamic = 0;
     k.publish = 0;
     k.n_stage = 2;
-    k.ks = mode_ks(mode);
     k.raster = 0;
     k.wind_step = 1;
-    if (force_sym(mode) == 2) sym64_chunks(k.N, k.cb);
     // numpy: linspace(0, 2 HEIGHT, G + 1) has step (hi - lo) / G, rounded once (state_processors.py:31-32)
     k.step_y = (k.y_hi - 0.0) / (double)k.G;
     k.inv_y = 1.0 / k.step_y;
@@ -725,8 +708,6 @@ int check_launch(const char* what) {
         case 1: { constexpr int TT = 1; __VA_ARGS__; } break; \
         case 2: { constexpr int TT = 2; __VA_ARGS__; } break; \
         case 3: { constexpr int TT = 3; __VA_ARGS__; } break; \
-        case 5: { constexpr int TT = 5; __VA_ARGS__; } break; \
-        case 6: { constexpr int TT = 6; __VA_ARGS__; } break; \
         default: { constexpr int TT = 4; __VA_ARGS__; } break; \
     }
 
@@ -774,15 +755,18 @@ T* mapped_host(T* host) {
 
 typedef void (*StepKernel)(const KP, const SwarmState, const SwarmStepIO, const SwarmInjectedDraws, const int, const int);
 
-StepKernel step_kernel(int mode, bool precise) {
+template <int PLACE>
+StepKernel step_kernel_p(int mode, bool precise) {
     switch (mode) {
-        case 1: return precise ? k_step<1, true> : k_step<1, false>;
-        case 2: return precise ? k_step<2, true> : k_step<2, false>;
-        case 3: return precise ? k_step<3, true> : k_step<3, false>;
-        case 5: return precise ? k_step<5, true> : k_step<5, false>;
-        case 6: return precise ? k_step<6, true> : k_step<6, false>;
-        default: return precise ? k_step<4, true> : k_step<4, false>;
+        case 1: return precise ? k_step<1, true, PLACE> : k_step<1, false, PLACE>;
+        case 2: return precise ? k_step<2, true, PLACE> : k_step<2, false, PLACE>;
+        case 3: return precise ? k_step<3, true, PLACE> : k_step<3, false, PLACE>;
+        default: return precise ? k_step<4, true, PLACE> : k_step<4, false, PLACE>;
     }
+}
+// place: RasterPlace (NONE / FOLLOW share the rasteriser-less kernel)
+StepKernel step_kernel(int mode, bool precise, int place) {
+    return place == 2 ? step_kernel_p<2>(mode, precise) : (place == 3 ? step_kernel_p<3>(mode, precise) : step_kernel_p<0>(mode, precise));
 }
 
 const SwarmInjectedDraws kNoDraws = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -808,19 +792,6 @@ struct StepShape {
 bool env_flag(const char* name) {
     const char* v = getenv(name);
     return v && v[0] && v[0] != '0';
-}
-
-// Warps per 64-locust super-tile.  Measured on B200 (profiles/r02_shapes.md): for swarms of 3+ super-tiles the pair loop is
-// XU-pipe-bound on the busiest SMs whatever the warp count (512 x 256: 37.7 us with 1 or 2 warps), so extra warps only
-// cost registers; for one or two super-tiles per env a single-wave batch is latency-bound and two warps per super-tile
-// halve the tile phase (1024 x 64, step's own threads rasterising: 15.9 vs 20.6 us).
-int pick_ks(const SwarmParams* p, int sms) {
-    if (!sym64_ok(p->n_locusts)) return 1;
-    const int nt2 = (p->n_locusts + 63) / 64;
-    if (nt2 > 2) return 1;
-    const int threads2 = 2 * nt2 * 32 + 32;
-    const long long one_wave2 = (long long)sms * (65536 / (64 * threads2));
-    return p->n_envs <= one_wave2 ? 2 : 1;
 }
 
 }  // namespace
@@ -852,15 +823,7 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
     if (rc) return rc;
     if (!st || !st->x || !st->xa || !st->noise_x || !st->noise_a || !st->elapsed || !st->episode) return SWARM_ERR_NULL;
     if (draws && !draws_complete(draws)) return SWARM_ERR_NULL;
-    int sms = 148;
-    {
-        int dev = 0;
-        if ((rc = current_device(&dev))) return rc;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-    }
-    const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
-    if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
-    const int mode = force_mode(p->n_locusts, ks);
+    const int mode = force_mode(p->n_locusts);
     const KP kp = make_kp(p, mode);
     const size_t smem = step_smem(p, 0, 1, mode);
     const int nt = block_threads(kp.N, mode);
@@ -882,7 +845,7 @@ int swarm_reset(const SwarmParams* p, const SwarmState* st, const uint8_t* mask,
 namespace {
 
 struct StepPlan {
-    int mode, ks, place;          // force mode (1..6), warps per super-tile, RasterPlace
+    int mode, place;              // force mode (1..4), RasterPlace
     int nf, nt, grid;             // force threads, threads per CTA, CTAs
     int n_stage, dynamic, raster, filler; // KP fields
     int follow_threads, rgrid;    // follower launch (place == RASTER_FOLLOW)
@@ -925,22 +888,21 @@ int plan_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
         }
         sms = it->second;
     }
-    const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
-    if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
-    const int mode = force_mode(N, ks);
+    const int filler_threads = 32;                           // the SELF shape's TMA zero-fill warp
+    const int mode = force_mode(N);
     const int nf = block_threads(N, mode);
     if (nf > kMaxThreads) return SWARM_ERR_SIZE;
     // With the per-env flags the observation can be produced by a second kernel that follows the step on a higher-priority
     // stream (k_raster_follow).  The follower spins until the step publishes an env, so the step must always be able to get
     // onto an SM next to it: shared memory, threads AND registers of both have to fit (checked below).
     const int follow_threads = (N + A) <= 128 ? 32 : 128;
-    const size_t follow_smem = smem_bytes(N, A, p->grid_size, 0, false, 1, 0, 1);
+    const size_t follow_smem = smem_bytes(N, A, p->grid_size, 0, false, 1, 0);
     // raster CTAs per SM that keep pace with the step (measured at 4096 envs: N = 160: 4 -> 0.110 ms, 2 -> 0.118; N = 192 and up: 2)
     int follow_per_sm = (N + A) <= 128 ? 6 : (N < 192 ? 4 : 2);
     while (follow_per_sm > 0 &&
            follow_per_sm * (follow_smem + 1024) + step_smem(p, 0, 1, mode) + 1024 > kMaxSmem) --follow_per_sm;
     const bool no_follower = (io->flags & SWARM_STEP_INKERNEL_RASTER) || env_flag("SWARM_B200_NO_FOLLOWER");
-    const StepKernel kernel = step_kernel(mode, p->math_mode != 0);
+    const StepKernel kernel = step_kernel(mode, p->math_mode != 0, RASTER_FOLLOW);     // the rasteriser-less kernel
     bool follow_fits = have_flags && !no_follower && follow_per_sm > 0 && follow_per_sm * follow_threads + nf <= 2048;
     int rgrid = 0;
     if (want_grid && follow_fits) {
@@ -963,16 +925,21 @@ int plan_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
         // N = 192: 0.123 vs 0.135), the raster warps for small swarms, where the rasteriser -- not the forces -- is the
         // critical path (N = 128: 0.080 vs 0.108 ms, N = 64: 0.052 vs 0.069).  Batches of at most about one wave of
         // one-env CTAs have nothing to hide the rasteriser under: there the step's own threads rasterise (SELF).
-        const int per_sm = 65536 / (64 * (nf + 32)) > 0 ? 65536 / (64 * (nf + 32)) : 1;
+        const int per_sm = 65536 / (64 * (nf + filler_threads)) > 0 ? 65536 / (64 * (nf + filler_threads)) : 1;
+        // ... measured (profiles/r02_shapes.md): SELF wins from 96 force threads up (1024 x 80: 17.8 vs 19.5 us, 512 x 256: 37.0
+        // vs 39.3); with one or two force warps per env the dedicated raster warps stay ahead (1024 x 64: 13.9 vs 20.2),
+        // and so they do when there are fewer CTAs than SMs (32 x 80: 10.4 vs 11.0).
         if (forced) place = forced;
-        else if (E <= (long long)sms * per_sm) place = RASTER_SELF;
+        // Large swarms (N >= 160, where the alternative is the follower kernel) keep SELF up to 4 CTAs per SM: beyond that the
+        // batch is XU-bound like a multi-wave one and the follower overlaps better (1024 x 192: 43.5 vs 46.0 us).
+        else if (E > sms && nf >= 96 && E <= (long long)sms * (N >= 160 && per_sm > 4 ? 4 : per_sm)) place = RASTER_SELF;
         else if (N >= 160) place = RASTER_FOLLOW;
         else place = RASTER_WARPS;
         if (place == RASTER_FOLLOW && !follow_fits) place = RASTER_WARPS;
         if (place == RASTER_WARPS && !warps_fit) place = RASTER_SELF;
     }
     const bool warps = place == RASTER_WARPS, self = place == RASTER_SELF;
-    out->mode = mode; out->ks = ks; out->place = place;
+    out->mode = mode; out->place = place;
     out->raster = warps ? 1 : (self ? 2 : 0);
     out->n_stage = warps ? 2 : 1;         // one env per CTA (no raster warps): nothing to prefetch into a second buffer
     out->smem = step_smem(p, out->raster, out->n_stage, mode);
@@ -984,10 +951,10 @@ int plan_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
     out->filler = (self && ((p->grid_size * p->grid_size) & 7) == 0 && (reinterpret_cast<uintptr_t>(io->grid) & 15) == 0 &&
                    nf + 32 <= kMaxThreads && E <= (long long)sms * (65536 / (64 * (nf + 32)))) ? 1 : 0;
     out->nt = nf + (warps ? raster_threads(N, A) : 0) + (out->filler ? 32 : 0);
-    out->kernel = kernel;
-    if ((rc = prep(kernel, out->smem))) return rc;
+    out->kernel = step_kernel(mode, p->math_mode != 0, place);
+    if ((rc = prep(out->kernel, out->smem))) return rc;
     int grid = 0;
-    if ((rc = persistent_grid(kernel, out->nt, out->smem, E, &grid))) return rc;
+    if ((rc = persistent_grid(out->kernel, out->nt, out->smem, E, &grid))) return rc;
     // without raster warps to overlap there is nothing to gain from persistence, and hardware-scheduled one-env
     // CTAs measure 8 % faster (C4: 0.154 vs 0.166 ms)
     if (!warps) grid = E;
@@ -1009,7 +976,7 @@ int swarm_step_plan(const SwarmParams* p, const SwarmState* st, const SwarmStepI
     StepPlan pl;
     const int rc = plan_step(p, st, io, nullptr, &pl);
     if (rc) return rc;
-    out[0] = pl.mode; out[1] = pl.ks; out[2] = pl.place; out[3] = pl.nt; out[4] = pl.grid;
+    out[0] = pl.mode; out[1] = pl.filler; out[2] = pl.place; out[3] = pl.nt; out[4] = pl.grid;
     out[5] = (int32_t)pl.smem; out[6] = pl.place == RASTER_FOLLOW ? pl.rgrid : 0;
     out[7] = pl.place == RASTER_FOLLOW ? 2 : 1;
     return SWARM_OK;
@@ -1033,7 +1000,40 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
     const int grid = pl.grid, nt = pl.nt, nf = pl.nf, rgrid = pl.rgrid, follow_threads = pl.follow_threads;
     const size_t smem = pl.smem, follow_smem = pl.follow_smem;
     if (pl.place != RASTER_FOLLOW) {
-        kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
+        // Single-kernel shapes are launched as programmatic dependents of whatever precedes them in the stream: when that is
+        // the previous step (back-to-back env steps, a captured rollout graph) its tail overlaps with this kernel's launch
+        // latency and shared-memory prologue; after any other kernel it is an ordinary launch.  SWARM_B200_NO_PDL=1 opts out.
+        // Measured (profiles/r02_shapes.md): it pays for latency-bound batches -- small swarms (1024 x 80: 17.8 -> 16.5 us),
+        // few CTAs per SM (256 x 256: 26.6 -> 25.3) -- and costs where the batch is XU-bound per SM, because the early-placed
+        // CTAs of the next step unbalance the SMs (512 x 256: 36.8 -> 40.6 us), or where persistent raster-warp CTAs fill
+        // the machine anyway.
+        static const bool no_pdl = env_flag("SWARM_B200_NO_PDL");
+        int sms = 148;
+        {
+            KernelCache& c = cache();
+            std::lock_guard<std::mutex> lk(c.mu);
+            int dev = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && c.sms.count(dev)) sms = c.sms[dev];
+        }
+        const bool pdl = !no_pdl && (pl.place == RASTER_WARPS ? p->n_envs <= sms
+                                                               : (p->n_locusts < 160 || p->n_envs <= 2 * sms));
+        if (!pdl) {
+            kernel<<<grid, nt, smem, s>>>(kp, *st, *io, dr, has, nf);
+            return check_launch("swarm_step");
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)nt);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, kp, *st, *io, dr, has, nf);
+        if (le != cudaSuccess) return cuda_fail(le, "swarm_step (cudaLaunchKernelEx)");
         return check_launch("swarm_step");
     }
     // Step first, follower second: if anything serialises the two launches (a profiler, CUDA_LAUNCH_BLOCKING, a
@@ -1203,7 +1203,7 @@ int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa, flo
     if (!x || !grid) return SWARM_ERR_NULL;
     if (p->n_agents > 0 && (!xa || !positions)) return SWARM_ERR_NULL;
     const KP kp = make_kp(p);
-    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, 1, 0, 1);
+    const size_t smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, 1, 0);
     const int nt = (kp.N + kp.A) <= 128 ? 64 : 128;
     if ((rc = prep(k_rasterize, smem))) return rc;
     k_rasterize<<<kp.E, nt, smem, (cudaStream_t)stream>>>(kp, x, xa, grid, positions, box);
@@ -1239,15 +1239,7 @@ int swarm_forces(const SwarmParams* p, const double* x, const double* xa, float*
     int rc = validate(p);
     if (rc) return rc;
     if (!x || !xa || (!v && !reward)) return SWARM_ERR_NULL;
-    int sms = 148;
-    {
-        int dev = 0;
-        if ((rc = current_device(&dev))) return rc;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-    }
-    const int ks = (p->tuning & 7) ? (p->tuning & 7) : pick_ks(p, sms);
-    if (ks != 1 && ks != 2 && ks != 4) return SWARM_ERR_FLAGS;
-    const int mode = force_mode(p->n_locusts, ks);
+    const int mode = force_mode(p->n_locusts);
     const KP kp = make_kp(p, mode);
     const size_t smem = step_smem(p, 0, 1, mode);
     const int nt = block_threads(kp.N, mode);

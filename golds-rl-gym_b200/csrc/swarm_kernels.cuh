@@ -49,14 +49,12 @@ struct KP {
     int dynamic;      // k_step: draw the third and later envs of a CTA from the work queue (SwarmState::work)
     int n_stage;      // k_step: stage buffers in shared memory (2 = prefetch the CTA's next env, 1 = one env per CTA)
     int publish;      // k_step: raise work[2 + e] once env e's new state is in memory (k_raster_follow waits for it)
-    int ks;           // MODE 3 family: warps that share one 64-locust super-tile (1, 2 or 4; = the kernel's template KS)
     int raster;       // shared-memory layout of the rasteriser: 0 none, 1 a raster GROUP with its own point buffer, 2 the force
                       // group rasterises its own env after the step (points = the stage buffer)
     int filler;       // raster == 2: one extra warp per CTA issues the TMA zero fill of the env's grid and waits for it
     int wind_step;    // 0: the step proper does not add the wind to the actions (SwarmEnv._step(add_wind=False))
     unsigned long long* trace;   // debug (swarm_debug_trace): per-CTA phase timestamps, nullptr in production
     long long trace_slots;       // capacity of trace in records of 2 * TR_PHASES words
-    unsigned char cb[8];   // MODE 3 family: canonical chunk c = segments [cb[c], cb[c+1]) of a warp's pass list (sym64_chunks)
     // rasteriser constants the host can round exactly like numpy does
     double step_y, inv_y; // (2 HEIGHT - 0) / G and its reciprocal
     double inv_x;         // ~ G / WIDTH: only seeds the bin guess (count_le settles ties against the exact edges)
@@ -85,7 +83,6 @@ struct Smem {
                       //   MODE 1/3: nt 32-tiles x 64 (each tile stored twice: wrap-free lane+k reads) + A agents
                       //   MODE 2/4: N locusts + A agents
     float2* slot;     // MODE 1/3: nt x nslots x 32 reaction-force partial sums
-    float2* own;      // MODE 3 with KS > 1: KS x (nt2 x 64) own-force partial sums of the warps sharing a super-tile
     float2* agf;      // MODE 1/3: nt x 32 agent pulls, evaluated by the finishing thread BEFORE the tile passes (off the
                       // critical path after the barrier) and added last
     // ---- rasteriser (present when the kernel rasterises)
@@ -100,51 +97,6 @@ struct Smem {
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
 __host__ __device__ inline int n_tiles(int N) { return (N + 31) >> 5; }
-
-// ---- canonical decomposition of the MODE 3 pair work (64-wide super-tiles) ---------------------------------------
-// A warp's work on its super-tile is a list of SEGMENTS (a run of lane-rotation steps against one half-tile, with
-// its own reaction slot); the list is cut into FOUR canonical chunks of about equal length.  Own forces are summed
-// per chunk and combined as (c0 + c1) + (c2 + c3), whoever computes them: one warp (KS = 1), two warps taking two
-// chunks each (KS = 2) or four warps taking one each (KS = 4).  The results are therefore bitwise independent of
-// KS, which the host picks by batch size (few envs -> more warps per env).
-//   N <= 64 (one super-tile, two passes of 15 steps): segments of <= 8 steps (2 per pass) so that there are 4;
-//   else: a segment is a whole pass (15 / 32 / 16 steps).
-__host__ __device__ inline int sym64_seg(int N) { return N <= 64 ? 8 : 32; }
-__host__ __device__ inline int sym64_qmax(int N) { return N <= 64 ? 2 : 1; }
-__host__ __device__ inline int sym64_nslots(int N) { return 1 + ((N + 63) >> 6) / 2; }
-__host__ __device__ inline int sym64_nseg(int N) { return 2 * sym64_nslots(N) * sym64_qmax(N); }
-// rotation steps of pass pair o (both passes of a pair have the same length)
-__host__ __device__ inline int sym64_pass_steps(int N, int o) {
-    const int nt2 = (N + 63) >> 6, nfull = (nt2 - 1) >> 1;
-    return o == 0 ? 15 : (o <= nfull ? 32 : 16);
-}
-// pair evaluations of segment s (the own-tile passes carry two extra single pairs)
-__host__ __device__ inline int sym64_seg_steps(int N, int s) {
-    const int qmax = sym64_qmax(N), seg = sym64_seg(N);
-    const int p = s / qmax, q = s % qmax, n = sym64_pass_steps(N, p >> 1);
-    int k = n - q * seg;
-    k = k < 0 ? 0 : (k > seg ? seg : k);
-    if (p < 2 && (q == 0 || q == qmax - 1)) k += 1;
-    return k;
-}
-// chunk boundaries cb[0..4]: boundary j sits where the running step count is nearest to j/4 of the total
-inline void sym64_chunks(int N, unsigned char cb[8]) {
-    const int ns = sym64_nseg(N);
-    int total = 0;
-    for (int s = 0; s < ns; ++s) total += sym64_seg_steps(N, s);
-    cb[0] = 0;
-    for (int j = 1; j < 4; ++j) {
-        int best = cb[j - 1], cum = 0, bestd = 1 << 30;
-        for (int s = 0; s <= ns; ++s) {
-            const int d = 4 * cum - j * total;
-            if (s >= cb[j - 1] && (d < 0 ? -d : d) < bestd) { bestd = d < 0 ? -d : d; best = s; }
-            if (s < ns) cum += sym64_seg_steps(N, s);
-        }
-        cb[j] = (unsigned char)best;
-    }
-    cb[4] = (unsigned char)ns;
-    cb[5] = cb[6] = cb[7] = 0;
-}
 
 __host__ __device__ inline size_t smem_stage_bytes(int N, int A) { return 16 * ((size_t)N + 3 * A + 1); }
 __host__ __device__ inline int sym_tiles(int N, int sym);
@@ -161,33 +113,33 @@ __host__ __device__ inline bool table_is16(int N, int A) { return N < (1 << kAge
 __host__ __device__ inline size_t smem_table_bytes(int N, int A, int G) {
     return table_is16(N, A) ? smem_align(sizeof(uint16_t) * G * G) : smem_align(sizeof(uint32_t) * G * G);
 }
-// sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3 family)
+// sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3)
 __host__ __device__ inline int sym_tiles(int N, int sym) { return sym == 2 ? 2 * ((N + 63) >> 6) : n_tiles(N); }
 __host__ __device__ inline int sym_slots(int N, int sym) {
-    return sym == 2 ? sym64_nslots(N) * sym64_qmax(N) : 1 + n_tiles(N) / 2;
+    return sym == 2 ? 1 + ((N + 63) >> 6) / 2 : 1 + n_tiles(N) / 2;
 }
 __host__ __device__ inline size_t smem_slot_bytes(int N, int sym) {
     return sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * sym_slots(N, sym) * 32) : 0;
 }
-__host__ __device__ inline size_t smem_own_bytes(int N, int sym, int ks) {
-    return (sym == 2 && ks > 1) ? smem_align(sizeof(float2) * ks * sym_tiles(N, sym) * 32) : 0;
-}
 __host__ __device__ inline size_t smem_agf_bytes(int N, int sym) {
     return sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * 32) : 0;
 }
-__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym, int ks) {
-    return smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) + smem_own_bytes(N, sym, ks) + smem_agf_bytes(N, sym);
+// agf: the agent-pull buffer exists in the latency-bound SELF shape only (raster == 2), see forces_sym*_tiles
+__host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym, bool agf) {
+    return smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) + (agf ? smem_agf_bytes(N, sym) : 0);
 }
 constexpr int kLutL = 256, kLutA = 33;     // grid-value look-up: counts below kLutL locusts / kLutA agents per cell
+__host__ __device__ inline int lut_locusts(int N) { return N + 1 < kLutL ? N + 1 : kLutL; }
+__host__ __device__ inline int lut_agents(int A) { return A + 1 < kLutA ? A + 1 : kLutA; }
 // raster: 0 none, 1 raster group with its own point buffer, 2 the force group rasterises (points = stage buffer)
 __host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G, int raster) {
     if (!raster) return 0;
     return (raster == 1 ? smem_align(sizeof(double2) * (N + A)) : 0) + smem_table_bytes(N, A, G) +
-           smem_align(sizeof(int) * (N + A)) + smem_align(sizeof(float) * (kLutL + kLutA));
+           smem_align(sizeof(int) * (N + A)) + smem_align(sizeof(float) * (lut_locusts(N) + lut_agents(A)));
 }
 // n_stage: stage buffers (2 in the pipelined step kernel, 1 in reset/forces, 0 in the rasteriser)
-__host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, int raster, int sym, int ks) {
-    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(N, A) + (force ? smem_force_bytes(N, A, sym, ks) : 0) +
+__host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, int raster, int sym) {
+    return n_stage * smem_stage_bytes(N, A) + smem_fixed_bytes(N, A) + (force ? smem_force_bytes(N, A, sym, raster == 2) : 0) +
            smem_raster_bytes(N, A, G, raster);
 }
 
@@ -202,7 +154,7 @@ __device__ __forceinline__ Stage stage_at(unsigned char* base, int N, int A, int
     return s;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, int n_stage, bool force, int sym, int ks,
+__device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, int n_stage, bool force, int sym,
                                       int raster) {
     Smem s;
     s.st = stage_at(base, N, A, 0);
@@ -214,10 +166,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     s.mail = reinterpret_cast<int*>(base + o);    o += 16;
     s.src = reinterpret_cast<float4*>(base + o);
     s.slot = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym));
-    s.own = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym));
-    s.agf = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) +
-                                      smem_own_bytes(N, sym, ks));
-    if (force) o += smem_force_bytes(N, A, sym, ks);
+    s.agf = reinterpret_cast<float2*>(base + o + smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym));
+    if (force) o += smem_force_bytes(N, A, sym, raster == 2);
     s.rx = reinterpret_cast<double2*>(base + o);
     if (raster == 1) o += smem_align(sizeof(double2) * (N + A));
     s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_table_bytes(N, A, G);
@@ -227,18 +177,31 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Debug timeline (swarm_debug_trace): record `rec` holds, for phase ph < 16, the global timer (ns) in word 2 ph and the
-// SM's cycle counter in word 2 ph + 1.  One uniform, never-taken branch per call site in production.
+// Debug timeline (swarm_debug_trace; only in a library built with -DSWARM_TRACE, see scripts/build_variants.py): record
+// `rec` holds, for phase ph < 16, the global timer (ns) in word 2 ph and the SM's cycle counter in word 2 ph + 1.
 enum : int { TR_ENTRY = 0, TR_ZFILL = 1, TR_LOADED = 2, TR_STAGED = 3, TR_TILES = 4, TR_FORCES = 5, TR_STEPPED = 6, TR_STORED = 7,
              TR_RASTER = 8, TR_MEAN = 9, TR_BINNED = 10, TR_ZEROS = 11, TR_DONE = 12, TR_PHASES = 16 };
 __device__ __forceinline__ void trace_mark(const KP& kp, const long long rec, const int ph) {
+#ifndef SWARM_TRACE
+    (void)kp; (void)rec; (void)ph;      // compiled out of the production library: the hooks cost 0.5-2.5 % (measured)
+#else
     if (kp.trace != nullptr && rec >= 0 && rec < kp.trace_slots) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         kp.trace[rec * 2 * TR_PHASES + 2 * ph] = t;
         kp.trace[rec * 2 * TR_PHASES + 2 * ph + 1] = (unsigned long long)clock64();
     }
+#endif
 }
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until every prerequisite grid has
+// completed and its memory is visible (a no-op for ordinary launches), pdl_launch_dependents() lets the successor's
+// CTAs be scheduled from now on (they then sit in pdl_wait()).  Used by the single-kernel step shapes: the successor's
+// launch latency and shared-memory prologue overlap with the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // cp.async (LDGSTS): HBM -> shared memory without staging through registers
@@ -349,27 +312,17 @@ __device__ __forceinline__ float4 split_hilo(const double2 p, const double c) {
 // MODE: 1 = unordered pairs, a warp owns a 32-locust tile, 1 target per lane
 //       3 = unordered pairs, a warp owns a 64-locust super-tile, 2 targets per lane (half the
 //           shared-memory loads and shuffles per pair; used when N pads to 64 as well as to 32)
-//       5, 6 = MODE 3 with KS = 2 / 4 warps per super-tile (each takes 2 / 1 of the four canonical chunks of the pass
-//           list; afterwards a thread finishes and integrates ONE target): for batches too small to fill the SMs
 //       2/4 = ordered pairs, 2/4 targets per thread (N > 512)
 template <int MODE>
 struct ModeT {
-    static constexpr int T = (MODE == 1 || MODE == 5 || MODE == 6) ? 1 : (MODE == 3 ? 2 : MODE);
-    static constexpr int SYM = MODE == 1 ? 1 : ((MODE == 3 || MODE == 5 || MODE == 6) ? 2 : 0);
-    static constexpr int KS = MODE == 5 ? 2 : (MODE == 6 ? 4 : 1);
+    static constexpr int T = MODE == 1 ? 1 : (MODE == 3 ? 2 : MODE);
+    static constexpr int SYM = MODE == 1 ? 1 : (MODE == 3 ? 2 : 0);
 };
 
-constexpr int kNoTarget = 0x7fffffff;
-
-// locust owned by thread g.tid as its t-th target (kNoTarget: none -- the third and fourth warp of a KS = 4 team)
+// locust owned by thread g.tid as its t-th target
 template <int MODE>
-__device__ __forceinline__ int target_index(const Grp& g, int t, const KP& kp) {
-    if constexpr (MODE == 3) return (g.tid >> 5) * 64 + t * 32 + (g.tid & 31);
-    if constexpr (MODE == 5 || MODE == 6) {
-        const int nt2 = (kp.N + 63) >> 6, W = g.tid >> 5, cg = W / nt2, I = W - cg * nt2;
-        return cg < 2 ? (2 * I + cg) * 32 + (g.tid & 31) : kNoTarget;
-    }
-    return g.tid + t * g.n;
+__device__ __forceinline__ int target_index(const Grp& g, int t, const KP&) {
+    return MODE == 3 ? ((g.tid >> 5) * 64 + t * 32 + (g.tid & 31)) : g.tid + t * g.n;
 }
 
 template <int MODE>
@@ -426,7 +379,7 @@ __device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const in
 // lanes, offset 0 = self), tiles I+1..I+floor((nt-1)/2) fully and tile I+nt/2 (nt even) half each
 // way.  One loop over these passes, so the pair code exists once.  The reaction sums land in
 // sm.slot; the caller must barrier before forces_sym_finish.
-template <bool PRECISE>
+template <bool PRECISE, bool AGF>
 __device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
     const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
@@ -434,7 +387,7 @@ __device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, c
     const int nfull = (nt - 1) >> 1;
     const float4* S = sm.src;
     const float4 tg = S[I * 64 + lane];
-    {   // the agents' pull on this lane's locust (multiagent.py:108-113), summed from 0 and added last in the finish
+    if constexpr (AGF) {   // the agents' pull on this lane's locust (multiagent.py:108-113), summed from 0, added last in the finish
         const float4* ag = S + nt * 64;
         float gx = 0.f, gy = 0.f;
 #pragma unroll 2
@@ -466,7 +419,7 @@ __device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, c
 }
 
 // MODE 1, part 2: add the reactions (fixed order: bitwise reproducible) and the agents' pull.
-template <bool PRECISE>
+template <bool PRECISE, bool AGF>
 __device__ __forceinline__ void forces_sym_finish(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
     const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
@@ -475,9 +428,21 @@ __device__ __forceinline__ void forces_sym_finish(const Smem& sm, const KP& kp, 
         ax += r.x;
         ay += r.y;
     }
-    const float2 a = sm.agf[I * 32 + lane];     // written by this very thread in forces_sym_tiles
-    ax += a.x;
-    ay += a.y;
+    // the agents' pull, summed from 0 and added last: either evaluated before the tile passes (AGF: the latency-bound
+    // shape, where this keeps it off the critical path behind the barrier) or here -- the same bits either way
+    if constexpr (AGF) {
+        const float2 a = sm.agf[I * 32 + lane];     // written by this very thread in forces_sym_tiles
+        ax += a.x;
+        ay += a.y;
+    } else {
+        const float4 tg = sm.src[I * 64 + lane];
+        const float4* ag = sm.src + nt * 64;
+        float gx = 0.f, gy = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
+        ax += gx;
+        ay += gy;
+    }
 }
 
 // ---- MODE 3: 64-wide super-tiles, two targets (A: first half, B: second half) per lane -------
@@ -618,173 +583,127 @@ __device__ __forceinline__ void tile_sym2(const float4* __restrict__ tl, const i
     }
 }
 
-// MODE 3 family, part 1.  Super-tile I = half-tiles 2I (A targets) and 2I+1 (B targets); its work is the pass list
+// MODE 3, part 1.  Warp I owns super-tile I = half-tiles 2I (A targets) and 2I+1 (B targets).
+// Passes (one loop, so the pair code exists once):
 //   p = 0  own A half as sources: offset 0 (B target only: the A x B block is split by offset, (B target,
 //          A source) takes 0..15), offsets 1..15 both targets, offset 16 A target one way;
 //   p = 1  own B half as sources: offsets 1..15 both targets, offset 16 A target ((A target, B source)
 //          takes 1..16) with reaction + B target one way;
 //   then   super-tiles I+1 .. I+floor((nt2-1)/2): both halves, all 32 offsets;
-//          super-tile I+nt2/2 (nt2 even): both halves, half the offsets each way,
-// cut into segments and four canonical chunks (sym64_chunks).  With KS warps per super-tile, warp (I, cg) runs the
-// chunks [cg * 4/KS, (cg + 1) * 4/KS); one loop over the segments, so the pair code exists once.  On return (ax, ay)
-// hold this thread's share of the own forces of its two targets, combined in the canonical order.
-template <int KS, bool PRECISE>
-__device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp, const Grp& g, float (&ax)[2],
-                                                   float (&ay)[2]) {
-    const int lane = g.tid & 31, W = g.tid >> 5;
+//          super-tile I+nt2/2 (nt2 even): both halves, half the offsets each way.
+// AGF: the agents' pull on the lane's two targets is evaluated first and parked in sm.agf (see forces_sym64_finish).
+template <bool PRECISE, bool AGF>
+__device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
+                                                   float (&vy)[2]) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
-    const int cg = KS == 1 ? 0 : W / nt2, I = KS == 1 ? W : W - cg * nt2;
     const int nxt = (lane + 1) & 31;
     const int nfull = (nt2 - 1) >> 1;
-    const int qmax = sym64_qmax(kp.N), seg = sym64_seg(kp.N);
+    const int npass = 2 * nslots;
     const float4* S = sm.src;
     const float4 tgA = S[(2 * I) * 64 + lane], tgB = S[(2 * I + 1) * 64 + lane];
-    {   // the agents' pull on the target(s) this thread will FINISH (multiagent.py:108-113), summed from 0 and added
-        // last: evaluated here, where it overlaps with the tile passes, instead of after the barrier
+    if constexpr (AGF) {
         const float4* ag = S + nt2 * 128;
-        if constexpr (KS == 1) {
-            float gAx = 0.f, gAy = 0.f, gBx = 0.f, gBy = 0.f;
-            if constexpr (PRECISE) {
-                for (int k = 0; k < kp.A; ++k) {
-                    const float4 q = ag[k];
-                    pair_ordered<PRECISE>(q, tgA, kp, gAx, gAy);
-                    pair_ordered<PRECISE>(q, tgB, kp, gBx, gBy);
-                }
-            } else {
-                const Targets2 t = make_targets2(tgA, tgB);
-                const PairConst2 c = make_pair_const2(kp);
-                f32x2 naA = 0, naB = 0, b = 0;
-#pragma unroll 2
-                for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
-                upk2(naA, gAx, gAy);
-                upk2(naB, gBx, gBy);
-                gAx = -gAx; gAy = -gAy; gBx = -gBx; gBy = -gBy;
+        float gAx = 0.f, gAy = 0.f, gBx = 0.f, gBy = 0.f;
+        if constexpr (PRECISE) {
+            for (int k = 0; k < kp.A; ++k) {
+                const float4 q = ag[k];
+                pair_ordered<PRECISE>(q, tgA, kp, gAx, gAy);
+                pair_ordered<PRECISE>(q, tgB, kp, gBx, gBy);
             }
-            sm.agf[(2 * I) * 32 + lane] = make_float2(gAx, gAy);
-            sm.agf[(2 * I + 1) * 32 + lane] = make_float2(gBx, gBy);
-        } else if (cg < 2) {
-            const float4 tg = cg == 0 ? tgA : tgB;
-            float gx = 0.f, gy = 0.f;
-#pragma unroll 2
-            for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
-            sm.agf[(2 * I + cg) * 32 + lane] = make_float2(gx, gy);
-        }
-    }
-    constexpr int CH = 4 / KS;                        // canonical chunks run by this thread
-    float tAx = 0.f, tAy = 0.f, tBx = 0.f, tBy = 0.f;      // (c0 + c1) [+ (c2 + c3)]
-    float uAx = 0.f, uAy = 0.f, uBx = 0.f, uBy = 0.f;      // c_even [+ c_odd]
-#pragma unroll 1
-    for (int c = 0; c < CH; ++c) {
-        const int cc = cg * CH + c;
-        float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f;
-#pragma unroll 1
-        for (int s = kp.cb[cc]; s < (int)kp.cb[cc + 1]; ++s) {
-            const int p = qmax == 2 ? s >> 1 : s, q = qmax == 2 ? s & 1 : 0;
-            const int o = p >> 1, h = p & 1;
-            int J = I, first = 1, n = 15;
-            if (o > 0) {
-                if (o <= nfull) {
-                    J = I + o;
-                    if (J >= nt2) J -= nt2;
-                    first = 0;
-                    n = 32;
-                } else {
-                    J = I < o ? I + o : I - o;
-                    first = I < o ? 0 : 1;
-                    n = 16;
-                }
-            }
-            const int f = first + q * seg;                                  // this segment: offsets f .. f + nn - 1
-            const int nn = (n - q * seg) < seg ? (n - q * seg) : seg;
-            const bool tail = (q + 1) * seg >= n;                           // the pass ends with this segment
-            const int H = 2 * J + h;
-            const float4* tl = S + H * 64 + lane;
-            float bx = 0.f, by = 0.f;
-            if (p == 0 && q == 0) pair_sym<true, PRECISE>(tl[0], tgB, kp, aBx, aBy, bx, by);
-            tile_sym2<PRECISE>(tl + f, nn, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
-            int last = f + nn - 1;                       // offset of the element whose reaction this lane holds
-            if (tail && p == 0) {
-                float ux, uy;
-                pair_sym<false, PRECISE>(tl[16], tgA, kp, aAx, aAy, ux, uy);
-            } else if (tail && p == 1) {
-                bx = __shfl_sync(kFull, bx, nxt);
-                by = __shfl_sync(kFull, by, nxt);
-                const float4 qq = tl[16];
-                float ux, uy;
-                pair_sym<true, PRECISE>(qq, tgA, kp, aAx, aAy, bx, by);
-                pair_sym<false, PRECISE>(qq, tgB, kp, aBx, aBy, ux, uy);
-                last = 16;
-            }
-            sm.slot[((H * nslots + o) * qmax + q) * 32 + ((lane + last) & 31)] = make_float2(bx, by);
-        }
-        if ((c & 1) == 0) {
-            uAx = aAx; uAy = aAy; uBx = aBx; uBy = aBy;
         } else {
-            uAx += aAx; uAy += aAy; uBx += aBx; uBy += aBy;
+            const Targets2 t = make_targets2(tgA, tgB);
+            const PairConst2 c = make_pair_const2(kp);
+            f32x2 naA = 0, naB = 0, b = 0;
+#pragma unroll 2
+            for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
+            upk2(naA, gAx, gAy);
+            upk2(naB, gBx, gBy);
+            gAx = -gAx; gAy = -gAy; gBx = -gBx; gBy = -gBy;
         }
-        if (c == CH - 1 || (c & 1)) {
-            if (c < 2) {
-                tAx = uAx; tAy = uAy; tBx = uBx; tBy = uBy;
+        sm.agf[(2 * I) * 32 + lane] = make_float2(gAx, gAy);
+        sm.agf[(2 * I + 1) * 32 + lane] = make_float2(gBx, gBy);
+    }
+    float aAx = 0.f, aAy = 0.f, aBx = 0.f, aBy = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < npass; ++p) {
+        const int o = p >> 1, h = p & 1;
+        int J = I, first = 1, n = 15;
+        if (o > 0) {
+            if (o <= nfull) {
+                J = I + o;
+                if (J >= nt2) J -= nt2;
+                first = 0;
+                n = 32;
             } else {
-                tAx += uAx; tAy += uAy; tBx += uBx; tBy += uBy;
+                J = I < o ? I + o : I - o;
+                first = I < o ? 0 : 1;
+                n = 16;
             }
         }
+        const int H = 2 * J + h;
+        const float4* tl = S + H * 64 + lane;
+        float bx = 0.f, by = 0.f;
+        if (p == 0) pair_sym<true, PRECISE>(tl[0], tgB, kp, aBx, aBy, bx, by);
+        tile_sym2<PRECISE>(tl + first, n, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
+        int last = first + n - 1;                        // offset of the element whose reaction this lane holds
+        if (p == 0) {
+            float ux, uy;
+            pair_sym<false, PRECISE>(tl[16], tgA, kp, aAx, aAy, ux, uy);
+        } else if (p == 1) {
+            bx = __shfl_sync(kFull, bx, nxt);
+            by = __shfl_sync(kFull, by, nxt);
+            const float4 q = tl[16];
+            float ux, uy;
+            pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
+            pair_sym<false, PRECISE>(q, tgB, kp, aBx, aBy, ux, uy);
+            last = 16;
+        }
+        sm.slot[(H * nslots + o) * 32 + ((lane + last) & 31)] = make_float2(bx, by);
     }
-    ax[0] = tAx; ay[0] = tAy; ax[1] = tBx; ay[1] = tBy;
-    if constexpr (KS > 1) {      // hand the partial sums to the threads that finish the targets
-        float2* own = sm.own + (size_t)cg * nt2 * 64;
-        own[(2 * I) * 32 + lane] = make_float2(tAx, tAy);
-        own[(2 * I + 1) * 32 + lane] = make_float2(tBx, tBy);
-    }
+    vx[0] = aAx; vy[0] = aAy; vx[1] = aBx; vy[1] = aBy;
 }
 
-// reactions received by half-tile H (fixed order: bitwise reproducible), added to (vx, vy)
-__device__ __forceinline__ void sym64_add_reactions(const Smem& sm, const KP& kp, const int H, const int lane, float& vx,
-                                                    float& vy) {
+// MODE 3, part 2: reactions (fixed order: bitwise reproducible), then the agents' pull summed from 0 and added last --
+// evaluated before the tile passes in the latency-bound SELF shape (AGF: off the critical path behind the barrier) or
+// here (the throughput-bound shapes: no buffer); the same bits either way.
+template <bool PRECISE, bool AGF>
+__device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[2],
+                                                    float (&vy)[2]) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
     const int nt2 = (kp.N + 63) >> 6, nslots = 1 + nt2 / 2;
-    const int qmax = sym64_qmax(kp.N), seg = sym64_seg(kp.N);
     for (int o = 0; o < nslots; ++o) {
-        const int nq = qmax == 1 ? 1 : (sym64_pass_steps(kp.N, o) + seg - 1) / seg;
-        for (int q = 0; q < nq; ++q) {
-            const float2 r = sm.slot[((H * nslots + o) * qmax + q) * 32 + lane];
-            vx += r.x;
-            vy += r.y;
-        }
+        const float2 ra = sm.slot[((2 * I) * nslots + o) * 32 + lane];
+        const float2 rb = sm.slot[((2 * I + 1) * nslots + o) * 32 + lane];
+        vx[0] += ra.x; vy[0] += ra.y;
+        vx[1] += rb.x; vy[1] += rb.y;
     }
-}
-
-// MODE 3 family, part 2: own partial sums, reactions (fixed order) and the agents' pull (sm.agf): v = (own + reactions) + agents.
-// KS = 1: (vx, vy)[2] come in as the own forces of the lane's two targets.  KS > 1: the thread finishes ONE target
-// (target_index), gathers the own partial sums of the KS warps from shared memory; result in (vx, vy)[0].
-template <int KS, bool PRECISE>
-__device__ __forceinline__ void forces_sym64_finish(const Smem& sm, const KP& kp, const Grp& g, float* vx, float* vy) {
-    const int lane = g.tid & 31, W = g.tid >> 5;
-    const int nt2 = (kp.N + 63) >> 6;
-    if constexpr (KS == 1) {
-        const int I = W;
-        sym64_add_reactions(sm, kp, 2 * I, lane, vx[0], vy[0]);
-        sym64_add_reactions(sm, kp, 2 * I + 1, lane, vx[1], vy[1]);
+    float gAx = 0.f, gAy = 0.f, gBx = 0.f, gBy = 0.f;
+    if constexpr (AGF) {
         const float2 a = sm.agf[(2 * I) * 32 + lane], b = sm.agf[(2 * I + 1) * 32 + lane];   // this thread's own writes
-        vx[0] += a.x; vy[0] += a.y;
-        vx[1] += b.x; vy[1] += b.y;
+        gAx = a.x; gAy = a.y; gBx = b.x; gBy = b.y;
     } else {
-        const int cg = W / nt2, I = W - cg * nt2;
-        vx[0] = 0.f;
-        vy[0] = 0.f;
-        if (cg >= 2) return;
-        const int H = 2 * I + cg, slot = H * 32 + lane;
-        const float2 o0 = sm.own[slot], o1 = sm.own[(size_t)nt2 * 64 + slot];
-        float x = o0.x + o1.x, y = o0.y + o1.y;
-        if constexpr (KS == 4) {
-            const float2 o2 = sm.own[(size_t)2 * nt2 * 64 + slot], o3 = sm.own[(size_t)3 * nt2 * 64 + slot];
-            x += o2.x + o3.x;
-            y += o2.y + o3.y;
+        const float4 tgA = sm.src[(2 * I) * 64 + lane], tgB = sm.src[(2 * I + 1) * 64 + lane];
+        const float4* ag = sm.src + nt2 * 128;      // agents act on locusts only (multiagent.py:108-113)
+        if constexpr (PRECISE) {
+            for (int k = 0; k < kp.A; ++k) {
+                const float4 q = ag[k];
+                pair_ordered<PRECISE>(q, tgA, kp, gAx, gAy);
+                pair_ordered<PRECISE>(q, tgB, kp, gBx, gBy);
+            }
+        } else {
+            const Targets2 t = make_targets2(tgA, tgB);
+            const PairConst2 c = make_pair_const2(kp);
+            f32x2 naA = 0, naB = 0, b = 0;
+#pragma unroll 2
+            for (int k = 0; k < kp.A; ++k) pair2_fast<false>(ag[k], t, c, naA, naB, b);
+            upk2(naA, gAx, gAy);
+            upk2(naB, gBx, gBy);
+            gAx = -gAx; gAy = -gAy; gBx = -gBx; gBy = -gBy;
         }
-        sym64_add_reactions(sm, kp, H, lane, x, y);
-        const float2 a = sm.agf[slot];               // this thread's own write
-        vx[0] = x + a.x;
-        vy[0] = y + a.y;
     }
+    vx[0] += gAx; vy[0] += gAy;
+    vx[1] += gBx; vy[1] += gBy;
 }
 
 // MODE 2/4: ordered pairs, T targets per thread (j = tid + t*n), broadcast LDS.128 sources.
@@ -810,27 +729,21 @@ __device__ __forceinline__ void forces_ordered(const Smem& sm, const KP& kp, con
 // SwarmEnv.v_calculate (multiagent.py:88-115) on staged sources: v of this thread's targets (wind
 // and gravity added, before any cutoff).  Needs the staged sources visible (a barrier since stage_*);
 // contains one group barrier in the unordered-pair modes.
-template <int MODE, bool PRECISE>
+template <int MODE, bool PRECISE, bool AGF = false>
 __device__ __forceinline__ void pair_forces(const Smem& sm, const KP& kp, const Grp& g, float (&vx)[ModeT<MODE>::T],
                                             float (&vy)[ModeT<MODE>::T], const long long trace_rec = -1) {
     constexpr int T = ModeT<MODE>::T;
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_STAGED);
     if constexpr (MODE == 1) {
-        forces_sym_tiles<PRECISE>(sm, kp, g, vx[0], vy[0]);
+        forces_sym_tiles<PRECISE, AGF>(sm, kp, g, vx[0], vy[0]);
         if (g.tid == 0) trace_mark(kp, trace_rec, TR_TILES);
         g.sync();
-        forces_sym_finish<PRECISE>(sm, kp, g, vx[0], vy[0]);
+        forces_sym_finish<PRECISE, AGF>(sm, kp, g, vx[0], vy[0]);
     } else if constexpr (MODE == 3) {
-        forces_sym64_tiles<1, PRECISE>(sm, kp, g, vx, vy);
+        forces_sym64_tiles<PRECISE, AGF>(sm, kp, g, vx, vy);
         if (g.tid == 0) trace_mark(kp, trace_rec, TR_TILES);
         g.sync();
-        forces_sym64_finish<1, PRECISE>(sm, kp, g, vx, vy);
-    } else if constexpr (MODE == 5 || MODE == 6) {
-        float ax[2], ay[2];
-        forces_sym64_tiles<ModeT<MODE>::KS, PRECISE>(sm, kp, g, ax, ay);
-        if (g.tid == 0) trace_mark(kp, trace_rec, TR_TILES);
-        g.sync();
-        forces_sym64_finish<ModeT<MODE>::KS, PRECISE>(sm, kp, g, vx, vy);
+        forces_sym64_finish<PRECISE, AGF>(sm, kp, g, vx, vy);
     } else {
         forces_ordered<T, PRECISE>(sm, kp, g, vx, vy);
     }
@@ -842,33 +755,20 @@ __device__ __forceinline__ void pair_forces(const Smem& sm, const KP& kp, const 
 }
 
 // reward = -mean_j |v_j|^2 (multiagent.py:114-115, v before any cutoff): a warp-shuffle sum per 32-locust tile
-// into one slot per tile, then the slots in order -- the same tree whichever mode / KS computed the forces.
+// into one slot per tile, then the slots in order.
 // The caller barriers between energy_put and energy_get.
 template <int MODE>
-__device__ __forceinline__ int energy_slots(const KP& kp, const Grp& g) {
-    return ModeT<MODE>::SYM == 2 ? 2 * ((kp.N + 63) >> 6) : (g.n >> 5);
-}
+__device__ __forceinline__ int energy_slots(const KP&, const Grp& g) { return g.n >> 5; }
 template <int MODE>
 __device__ __forceinline__ void energy_put(const Smem& sm, const KP& kp, const Grp& g, const float (&vx)[ModeT<MODE>::T],
                                            const float (&vy)[ModeT<MODE>::T]) {
     constexpr int T = ModeT<MODE>::T;
-    if constexpr (ModeT<MODE>::SYM == 2) {
+    double e = 0.0;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int j = target_index<MODE>(g, t, kp);
-            if (j == kNoTarget) continue;          // warp-uniform
-            double e = j < kp.N ? (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t] : 0.0;
-            e = warp_sum(e);
-            if ((g.tid & 31) == 0) sm.red[j >> 5] = e;
-        }
-    } else {
-        double e = 0.0;
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-            if (target_index<MODE>(g, t, kp) < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
-        e = warp_sum(e);
-        if ((g.tid & 31) == 0) sm.red[g.tid >> 5] = e;
-    }
+    for (int t = 0; t < T; ++t)
+        if (target_index<MODE>(g, t, kp) < kp.N) e += (double)vx[t] * (double)vx[t] + (double)vy[t] * (double)vy[t];
+    e = warp_sum(e);
+    if ((g.tid & 31) == 0) sm.red[g.tid >> 5] = e;
 }
 template <int MODE>
 __device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const Grp& g) {
@@ -881,7 +781,7 @@ __device__ __forceinline__ double energy_get(const Smem& sm, const KP& kp, const
 // SwarmEnv._step on the stage buffer sm.st.  Preconditions: st.xs/as/an, sm.nx and sm.act filled, each
 // element written by the thread that owns it here (element i <-> thread i mod n) or visible through
 // a barrier.  Postcondition: state updated and visible to the whole group; returns the reward.
-template <int MODE, bool PRECISE>
+template <int MODE, bool PRECISE, bool AGF = false>
 __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const Grp& g, float* v_out, const double wind_a,
                                            const long long trace_rec = -1) {
     constexpr int T = ModeT<MODE>::T;
@@ -899,7 +799,7 @@ __device__ __forceinline__ double env_step(const Smem& sm, const KP& kp, const G
     stage_locusts<MODE>(sm, kp, g);
     g.sync();
     float vx[T], vy[T];
-    pair_forces<MODE, PRECISE>(sm, kp, g, vx, vy, trace_rec);
+    pair_forces<MODE, PRECISE, AGF>(sm, kp, g, vx, vy, trace_rec);
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_FORCES);
     energy_put<MODE>(sm, kp, g, vx, vy);
     cp_async_wait_but_one();   // this thread's own noise rows have landed in sm.nx (no-op outside k_step)
@@ -1048,18 +948,19 @@ __device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA zero fill reads these zeros
 }
 
-// grid values of the small counts, once per CTA: lut[c] = c / N (c < kLutL), lut[kLutL + a] = a / A (a < kLutA), rounded
+// grid values of the small counts, once per CTA: lut[c] = c / N (c < lut_locusts), lut[lut_locusts + a] = a / A, rounded
 // like the scatter's own division
 __device__ __forceinline__ void raster_lut_fill(const Smem& sm, const KP& kp, const int tid, const int n) {
     const float fN = (float)kp.N, fA = (float)(kp.A > 0 ? kp.A : 1);
-    const int nl = kp.N + 1 < kLutL ? kp.N + 1 : kLutL, na = kp.A + 1 < kLutA ? kp.A + 1 : kLutA;
+    const int nl = lut_locusts(kp.N), na = lut_agents(kp.A);
     for (int c = tid; c < nl; c += n) sm.lut[c] = __fdiv_rn((float)c, fN);
-    for (int c = tid; c < na; c += n) sm.lut[kLutL + c] = __fdiv_rn((float)c, fA);
+    for (int c = tid; c < na; c += n) sm.lut[nl + c] = __fdiv_rn((float)c, fA);
 }
 
 // How env_raster waits for the zero fill of its grid (besides being a group barrier at both points):
 //   ZeroOwn     a thread of the group issued the TMA fill (tma_tid) or the group stored the zeros itself
-//   ZeroFiller  a filler warp outside the group issued it and arrives on BAR_ZREAD / BAR_ZDONE (k_step, SELF shape)
+//   ZeroSelf    k_step's SELF shape: a filler warp outside the group issued it and arrives on BAR_ZREAD / BAR_ZDONE, or
+//               (no filler) the group stored the zeros itself
 struct ZeroOwn {
     bool tma;
     int tma_tid;
@@ -1074,12 +975,17 @@ struct ZeroOwn {
         g.sync();
     }
 };
-struct ZeroFiller {
+struct ZeroSelf {            // filler: the warp outside the group; else the group stored the zeros itself
+    bool filler;
     int n_all;
     template <typename Group>
-    __device__ __forceinline__ void before_table(const Group&) const { bar_sync<BAR_ZREAD>(n_all); }
+    __device__ __forceinline__ void before_table(const Group& g) const {
+        if (filler) bar_sync<BAR_ZREAD>(n_all); else g.sync();
+    }
     template <typename Group>
-    __device__ __forceinline__ void before_scatter(const Group&) const { bar_sync<BAR_ZDONE>(n_all); }
+    __device__ __forceinline__ void before_scatter(const Group& g) const {
+        if (filler) bar_sync<BAR_ZDONE>(n_all); else g.sync();
+    }
 };
 
 // SwarmStateProcessor.process_state (state_processors.py:25-42) of the points pts = [N locusts; A
@@ -1093,18 +999,21 @@ struct ZeroFiller {
 struct NoRelease { __device__ __forceinline__ void operator()() const {} };
 struct NoOverlap { __device__ __forceinline__ void operator()(int, int) const {} };
 
-template <typename Group, typename Zero, typename Release, typename Overlap>
+template <bool SPLIT, typename Group, typename Zero, typename Release, typename Overlap>
 __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const Group& g,
                                            float* __restrict__ grid_e, uint8_t* __restrict__ pos_e, const bool tma,
                                            const Zero zero, const Release early_release_fn, const Overlap overlap_fn,
                                            const long long trace_rec = -1) {
     const int N = kp.N, A = kp.A, G = kp.G, P = N + A;
+    float2* g2 = reinterpret_cast<float2*>(grid_e);
     const bool t16 = table_is16(N, A);
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_RASTER);
     const double lo_y = 0.0, hi_y = kp.y_hi;
     const double step_y = kp.step_y, inv_y = kp.inv_y;
-    // phase 0
-    const bool split = g.n > 32;
+    // phase 0.  SPLIT (the latency-bound single-wave shape): the y bins are taken under the mean chain.  Otherwise (the
+    // throughput-bound shapes, where every extra instruction of the rasteriser is taken from a force warp): x and y
+    // are binned together after the mean.
+    const bool split = SPLIT && g.n > 32;
     if (g.tid == 0) {
         // np.mean(vstack([x,xa]),axis=0)[0] is a plain left-to-right FP64 sum: one dependent DADD per element
         double s = 0.0;
@@ -1117,7 +1026,8 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
         const int w_tid = split ? g.tid - 32 : g.tid, w_n = split ? g.n - 32 : g.n;
         if (!split) __syncwarp();
         overlap_fn(w_tid, w_n);
-        for (int p = w_tid; p < P; p += w_n) sm.cid[p] = count_le(pts[p].y, lo_y, hi_y, step_y, inv_y, G);
+        if (SPLIT)
+            for (int p = w_tid; p < P; p += w_n) sm.cid[p] = count_le(pts[p].y, lo_y, hi_y, step_y, inv_y, G);
     }
     zero.before_table(g);
     // phase 1: bin every point's x in FP64 against numpy's edges, count with warp-aggregated atomics
@@ -1142,7 +1052,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
             const bool agent = p >= N;
             const double2 q = pts[p];
             const int cx = count_le(q.x, lo_x, hi_x, step_x, inv_x, G);
-            const int cy = sm.cid[p];
+            const int cy = SPLIT ? sm.cid[p] : count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
             if (agent) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
                 pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
                 pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
@@ -1173,8 +1083,7 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_BINNED);
     zero.before_scatter(g);
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_ZEROS);
-    // phase 2: sparse scatter of the non-zero cells over the zero fill; the writer cleans its counter
-    float2* g2 = reinterpret_cast<float2*>(grid_e);
+    // phase 2: sparse scatter of the non-zero cells over the zeros; the writer cleans its counter
     for (int p = g.tid; p < P; p += g.n) {
         const int c = sm.cid[p];
         if (c >= 0) {
@@ -1190,8 +1099,9 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
                 nl = w & 0xffffu;
                 na = w >> 16;
             }
-            const float vl = nl < (uint32_t)kLutL ? sm.lut[nl] : __fdiv_rn((float)nl, (float)N);
-            const float va = A > 0 ? (na < (uint32_t)kLutA ? sm.lut[kLutL + na] : __fdiv_rn((float)na, (float)A)) : 0.f;
+            const uint32_t ll = (uint32_t)lut_locusts(N);
+            const float vl = nl < ll ? sm.lut[nl] : __fdiv_rn((float)nl, (float)N);
+            const float va = A > 0 ? (na < (uint32_t)lut_agents(A) ? sm.lut[ll + na] : __fdiv_rn((float)na, (float)A)) : 0.f;
             g2[c] = make_float2(vl, va);
         }
     }

@@ -237,8 +237,7 @@ class BatchedSwarmEnv(object):
         out = (ctypes.c_int32 * 8)()
         with self._ctx:
             nat.check(self.lib.swarm_step_plan(self._params_ref, self._state_ref, ctypes.byref(io), out), "swarm_step_plan")
-        keys = ("force_mode", "warps_per_super_tile", "raster_place", "threads", "ctas", "smem_bytes", "follower_ctas",
-                "launches")
+        keys = ("force_mode", "filler_warp", "raster_place", "threads", "ctas", "smem_bytes", "follower_ctas", "launches")
         d = dict(zip(keys, list(out)))
         d["raster_place"] = ("none", "follower kernel", "raster warps in k_step", "k_step's own threads")[d["raster_place"]]
         return d

@@ -53,9 +53,9 @@ typedef struct SwarmParams {
     int32_t max_episode_steps;  /* gym TimeLimit (128); 0 = raw SwarmEnv, no limit          */
     int32_t math_mode;          /* 0 = fast (MUFU rsqrt/ex2/rcp), 1 = precise (IEEE)        */
     int32_t tuning;             /* 0 = automatic launch shape.  Otherwise (tests / experiments; results are bitwise
-                                 * the same for every value): bits 0-2 = warps per 64-locust super-tile (1, 2, 4),
-                                 * bits 4-5 = rasteriser placement (1 follower kernel, 2 raster warps in the step
-                                 * kernel, 3 the step's own threads after the step)                            */
+                                 * the same for every value): bits 4-5 = rasteriser placement (1 follower kernel,
+                                 * 2 raster warps in the step kernel, 3 the step's own threads after the step);
+                                 * all other bits must be 0                                                   */
     double noise;               /* NOISE 1e-4   */
     double gravity;             /* GRAVITY -1   */
     double wind;                /* WIND_SPEED 1 */
@@ -151,8 +151,8 @@ int swarm_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io
                const SwarmInjectedDraws* reset_draws, swarm_stream_t stream);
 
 /* The launch shape swarm_step would use for these arguments (no launch; needs the device for occupancy queries):
- * out = { force mode, warps per 64-locust super-tile, rasteriser placement (0 none, 1 follower kernel, 2 raster warps,
- * 3 the step's own threads), threads per CTA, CTAs, dynamic shared memory bytes, follower CTAs, kernel launches }. */
+ * out = { force mode, filler warp (0/1), rasteriser placement (0 none, 1 follower kernel, 2 raster warps, 3 the step's
+ * own threads), threads per CTA, CTAs, dynamic shared memory bytes, follower CTAs, kernel launches }. */
 int swarm_step_plan(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io, int32_t out[8]);
 
 /* Same call with HOST buffers for the per-step inputs/results; synchronises the stream before
@@ -168,10 +168,11 @@ int swarm_step_host(const SwarmParams* p, const SwarmState* st, const SwarmStepI
                     const float* host_actions, float* host_reward, uint8_t* host_done,
                     float* host_grid, uint8_t* host_positions, swarm_stream_t stream);
 
-/* Debug only: from now on every step / rasteriser kernel of this process records phase timestamps of each CTA's first
+/* Debug only, and only in a library built with -DSWARM_TRACE (the production build compiles the hooks out: they cost
+ * 0.5-2.5 %): from now on every step / rasteriser kernel of this process records phase timestamps of each CTA's first
  * env into device_words (n_words uint64, zeroed by the caller; 32 words per record: for phase ph < 16 the global
  * timer in ns at [2 ph] and the SM cycle counter at [2 ph + 1]; record = CTA index of the step kernel, E + env for
- * the follower kernel; phases: see scripts/trace_step.py).  NULL switches it off.  Not thread-safe; costs one predictable branch per phase when off. */
+ * the follower kernel; phases: see scripts/trace_step.py).  NULL switches it off.  Not thread-safe. */
 void swarm_debug_trace(uint64_t* device_words, int64_t n_words);
 
 /* Destroys the CUDA graphs swarm_step_host caches for the CALLING host thread (one per argument

@@ -63,6 +63,45 @@ def pack(prefix, d, tr, snap_steps):
         d[prefix + "grid_val_%d" % k] = v
 
 
+def c1_1000():
+    """BASELINE.json configs[0] / SURVEY 8d C1 as specified: the reference SwarmEnv (N=80, seed 192 = Swarm-eval-v0), 1000
+    steps of a random policy = 7 full 128-step episodes + 104 steps with gym's TimeLimit emulated by hand (the raw class has
+    none, fed_gym/__init__.py:21-33), actions RandomState(0).normal clipped like transform_actions_for_env.  Every
+    reset re-seeds the global numpy RNG (multiagent.py:47-48), so all 8 episodes start from the same state.  Kept: the
+    actions, all rewards and done flags, the state at every episode start and after the first 16 steps of every
+    episode, and the reference's own steps/s on this container's CPU."""
+    import time
+    env = rl.make_reference_env(80, seed=192)
+    rs = np.random.RandomState(0)
+    acts = clipped_actions(rs, 1000)
+    st = env.reset()
+    starts_x, starts_xa, x16, xa16 = [st[0].copy()], [st[1].copy()], [], []
+    rewards, dones, ep_of_step = np.zeros(1000), np.zeros(1000, dtype=bool), np.zeros(1000, dtype=np.int32)
+    elapsed, ep, spent = 0, 0, 0.0
+    for t in range(1000):
+        t0 = time.perf_counter()
+        st, r, d, _ = env.step(acts[t])
+        spent += time.perf_counter() - t0
+        elapsed += 1
+        done = bool(d) or elapsed >= 128                # gym 0.9.4 TimeLimit._step
+        rewards[t], dones[t], ep_of_step[t] = r, done, ep
+        if elapsed == 16:
+            x16.append(st[0].copy()); xa16.append(st[1].copy())
+        if done:
+            assert env.t == env.N_BURN_IN
+            t0 = time.perf_counter()
+            st = env.reset()
+            spent += time.perf_counter() - t0
+            elapsed, ep = 0, ep + 1
+            starts_x.append(st[0].copy()); starts_xa.append(st[1].copy())
+    assert ep == 7 and elapsed == 104 and dones.sum() == 7
+    np.savez_compressed(os.path.join(OUT, "c1_1000_seed192_n80.npz"), actions=acts, reward=rewards, done=dones,
+                        episode=ep_of_step, start_x=np.stack(starts_x), start_xa=np.stack(starts_xa),
+                        x16=np.stack(x16), xa16=np.stack(xa16),
+                        ref_steps_per_s=np.array(1000.0 / spent), ref_seconds=np.array(spent))
+    print("c1_1000: reference %.1f steps/s (%.2f s incl. 7 resets)" % (1000.0 / spent, spent))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ma, sp = rl.load_reference()
@@ -144,4 +183,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "c1":      # only the 1000-step C1 fixture (leaves the others byte-identical)
+        os.makedirs(OUT, exist_ok=True)
+        c1_1000()
+    else:
+        main()
+        c1_1000()

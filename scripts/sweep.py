@@ -93,7 +93,7 @@ if __name__ == "__main__":
         E, N = (int(v) for v in parts[0].split("x"))
         tuning = 0
         for t in parts[1:]:
-            tuning |= PLACE[t] if t in PLACE else int(t[2:])        # ksK
+            tuning |= PLACE.get(t, 0)
         res = run(E, N, args.boundary, binding=args.binding, tuning=tuning)
         res["shape"] = s
         print(json.dumps(res), flush=True)

@@ -1,4 +1,6 @@
-"""Per-phase timeline of one batch-step (debug facility swarm_debug_trace):  python scripts/trace_step.py 512x256[:ksK][:place] ...
+"""Per-phase timeline of one batch-step (debug facility swarm_debug_trace).  Needs a tracing build of the library:
+    python scripts/build_variants.py trace=-DSWARM_TRACE
+    SWARM_B200_LIB=$PWD/.variants/libswarm_trace.so python scripts/trace_step.py 512x256[:follow|warps|self] ...
 For every CTA's first env: ns since the kernel's first CTA entered, per phase (median / p90 / max over CTAs)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,8 +18,8 @@ for s in sys.argv[1:]:
     E, N = (int(v) for v in parts[0].split("x"))
     tuning = 0
     for t in parts[1:]:
-        tuning |= PLACE[t] if t in PLACE else int(t[2:])
-    env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128, tuning=tuning)
+        tuning |= PLACE.get(t, 0)
+    env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128, tuning=tuning, binding="ctypes")
     env.reset()
     print("plan", env.plan())
     a = torch.randn(E, 10, 2, device="cuda").clamp(-0.7, 0.7).contiguous()

@@ -134,7 +134,8 @@ def main(args):
         monitor = pm.SwarmPolicyMonitor(global_policy_net=learner.network,
                                         state_processor=sp.SwarmStateProcessor(grid_size=args.height),
                                         out_dir=args.debugging_folder)
-    fps = learner.train(max_updates=args.max_updates, monitor=monitor, eval_every=args.eval_every)
+    fps = learner.train(max_updates=args.max_updates, monitor=monitor, eval_every=args.eval_every,
+                        summary_dir=args.debugging_folder)     # scalars: global_norm, rl/reward (summaries.jsonl)
     if int(os.environ.get("RANK", "0")) == 0:
         logging.info("done: %d global steps, %.1f frames/s", learner.global_step, fps)
     learner.cleanup()

@@ -132,16 +132,40 @@ def test_forces_and_step_every_tiling(M, N, mode):
     assert np.all(np.abs(gr.cpu().numpy() - rew) <= RTOL * np.abs(rew))
 
 
-@pytest.mark.parametrize("N", [64, 80])
-def test_reset_and_free_running_16_distribution(M, N):
-    """Free-running parity: injected reset (10 burn-in steps) then 16 steps, 128 seeds.
-    FP32 pair forces cannot hold 1e-5 on every seed (chaotic amplification): assert the
-    distribution (median, pass fraction) and record it; the committed seed list below must pass."""
+# Free-running parity.  Seeds 31000..31127 (128 of them) for N = 64 and N = 80: injected reset (10 burn-in steps), then 16
+# free-running steps from the oracle's post-reset state.  FP32 pair forces cannot hold rtol 1e-5 on EVERY seed -- the
+# dynamics amplify a perturbation by kappa = 2..700 over 16 steps (close pairs) -- so the contract is:
+#   * every seed NOT listed in KNOWN_CHAOTIC must pass rtol 1e-5 in fast math (the strict list: 126 + 128 seeds);
+#   * a listed seed must be explained by its measured kappa (err <= 2e-7 * kappa, 2e-7 being the single-step error
+#     bound observed in test_step_teacher_forced_16) and sit in the top decile of kappa;
+#   * the pass fraction may not drop below the measured level minus one seed.
+KNOWN_CHAOTIC = {64: set(), 80: {31021, 31125}, 256: None}       # None: report only (N = 256 has no strict list)
+MIN_PASS = {64: 127.0 / 128, 80: 125.0 / 128, 256: 0.0}
+
+
+def smooth_kappa(draws, E, actions_fn, eps=1e-10):
+    """Amplification of a perturbation of the oracle's post-reset state over the same 16 steps.  Only smooth directions
+    are perturbed: x everywhere, y of airborne locusts (lifting a grounded locust off y = 0 switches its wind on -- a
+    different trajectory, not a sensitivity)."""
+    x0, xa0 = so.reset_injected(*draws)
+    pert = eps * np.random.RandomState(1).normal(size=x0.shape)
+    pert[..., 1] *= x0[..., 1] > 0
+    xp, xq, xap, xaq = x0 + pert, x0.copy(), xa0.copy(), xa0.copy()
+    rs = np.random.RandomState(5)
+    for t in range(16):
+        a = actions_fn(rs).astype(np.float64)
+        so.step(xp, xap, a, draws[3][:, 10], draws[4][:, 10])
+        so.step(xq, xaq, a, draws[3][:, 10], draws[4][:, 10])
+    return np.array([np.abs(xp[e] - xq[e]).max() / eps for e in range(E)])
+
+
+@pytest.mark.parametrize("N", [64, 80, 256])
+def test_reset_and_free_running_16_seed_list(M, N):
     E = 128
     seeds = [31000 + e for e in range(E)]
     draws = stack_draws(seeds, N)
     inj = M.InjectedDraws(*draws, device="cuda")
-    out = {}
+    out = {"seeds": [seeds[0], seeds[-1]], "known_chaotic": sorted(KNOWN_CHAOTIC[N] or [])}
     for mode in ("fast", "precise"):
         env = M.BatchedSwarmEnv(E, n_locusts=N, max_episode_steps=0, math_mode=mode, auto_reset=False, rasterize=False)
         gx, gxa = env.reset(draws=inj)
@@ -152,37 +176,53 @@ def test_reset_and_free_running_16_distribution(M, N):
         # 16 free-running steps from the ORACLE's post-reset state
         load_state(env, x, xa, draws[3][:, 10], draws[4][:, 10])
         rs = np.random.RandomState(5)
+        worst_tf = 0.0
         for t in range(16):
             a = clipped(rs, (E, 10, 2))
             env.step(to_dev(a))
             so.step(x, xa, a.astype(np.float64), draws[3][:, 10], draws[4][:, 10])
         e16 = np.array([rel_err(env.x[e].cpu().numpy(), x[e]) for e in range(E)])
+        kappa = smooth_kappa(draws, E, lambda r: clipped(r, (E, 10, 2)))
+        bad = [int(seeds[e]) for e in np.nonzero(e16 > RTOL)[0]]
         out[mode] = dict(reset_median=float(np.median(e_reset)), reset_p90=float(np.percentile(e_reset, 90)),
                          reset_max=float(e_reset.max()), reset_pass=float((e_reset <= RTOL).mean()),
                          s16_median=float(np.median(e16)), s16_p90=float(np.percentile(e16, 90)),
-                         s16_max=float(e16.max()), s16_pass=float((e16 <= RTOL).mean()))
-        assert np.median(e16) <= 2e-6 and (e16 <= RTOL).mean() >= 0.90, out[mode]
-        assert np.median(e_reset) <= 2e-6 and (e_reset <= RTOL).mean() >= 0.90, out[mode]
-        # every seed above 1e-5 must be explained by the oracle's own sensitivity: perturb the FP64
-        # oracle's start by 1e-10 and measure the amplification kappa over the same 16 steps
-        bad = np.nonzero(e16 > RTOL)[0]
-        if len(bad):
-            x0p, xa0p = so.reset_injected(*draws)
-            xp = x0p + 1e-10 * np.random.RandomState(1).normal(size=x0p.shape)
-            xq, xaq, xap = x0p.copy(), xa0p.copy(), xa0p.copy()
+                         s16_max=float(e16.max()), s16_pass=float((e16 <= RTOL).mean()),
+                         kappa_median=float(np.median(kappa)), kappa_p90=float(np.percentile(kappa, 90)),
+                         kappa_max=float(kappa.max()),
+                         bad_seeds={s_: dict(err=float(e16[s_ - seeds[0]]), kappa=float(kappa[s_ - seeds[0]])) for s_ in bad})
+        os.makedirs(OUT, exist_ok=True)
+        with open(os.path.join(OUT, "parity_distribution_n%d.json" % N), "w") as f:
+            json.dump(out, f, indent=1)
+        if KNOWN_CHAOTIC[N] is None:
+            # N = 256 from a U[0,1)^2 start is a dense, strongly repelling swarm: the oracle itself amplifies a 1e-10
+            # perturbation by kappa ~ 1e7..1e10 over 16 steps, so no arithmetic narrower than the oracle's can track it
+            # free-running.  Reported (profiles/), not asserted; what holds at N = 256 is the teacher-forced per-step
+            # bound (test_step_teacher_forced_16, test_golden_trajectory_teacher_forced) -- re-measured here.
+            assert np.median(kappa) >= 1e4, out[mode]
+            xt, xat = so.reset_injected(*draws)
             rs = np.random.RandomState(5)
+            worst = 0.0
             for t in range(16):
-                a = clipped(rs, (E, 10, 2)).astype(np.float64)
-                so.step(xp, xap, a, draws[3][:, 10], draws[4][:, 10])
-                so.step(xq, xaq, a, draws[3][:, 10], draws[4][:, 10])
-            kappa = np.array([np.abs(xp[e] - xq[e]).max() / 1e-10 for e in range(E)])
-            out[mode]["kappa_median"] = float(np.median(kappa))
-            out[mode]["bad_seeds"] = {int(seeds[e]): dict(err=float(e16[e]), kappa=float(kappa[e])) for e in bad}
-            for e in bad:   # err <= C * kappa * 2^-24 * max|x| with C = 30
-                assert e16[e] * np.abs(x[e]).max() <= 30 * kappa[e] * 6e-8, (seeds[e], e16[e], kappa[e])
-    os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, "parity_distribution_n%d.json" % N), "w") as f:
-        json.dump(out, f, indent=1)
+                a = clipped(rs, (E, 10, 2))
+                load_state(env, xt, xat, draws[3][:, 10], draws[4][:, 10])
+                env.step(to_dev(a))
+                so.step(xt, xat, a.astype(np.float64), draws[3][:, 10], draws[4][:, 10])
+                worst = max(worst, max(rel_err(env.x[e].cpu().numpy(), xt[e]) for e in range(E)))
+            out[mode]["teacher_forced_16_worst_step"] = worst
+            with open(os.path.join(OUT, "parity_distribution_n%d.json" % N), "w") as f:
+                json.dump(out, f, indent=1)
+            assert worst <= STEP_TOL, worst
+            continue
+        assert np.median(e16) <= 2e-6 and np.median(e_reset) <= 2e-6, out[mode]
+        assert (e16 <= RTOL).mean() >= MIN_PASS[N] - (1.0 / 128 if mode == "precise" else 0.0), out[mode]
+        assert (e_reset <= RTOL).mean() >= 0.98, out[mode]
+        for s_ in bad:          # every failing seed is explained by the oracle's own sensitivity
+            e = s_ - seeds[0]
+            assert e16[e] <= 2e-7 * kappa[e], (s_, e16[e], kappa[e])
+            assert kappa[e] >= np.percentile(kappa, 90), (s_, kappa[e])
+        if mode == "fast" and KNOWN_CHAOTIC[N] is not None:
+            assert set(bad) <= KNOWN_CHAOTIC[N], "seeds off the strict list fail rtol 1e-5: %s" % sorted(set(bad) - KNOWN_CHAOTIC[N])
 
 
 @pytest.mark.parametrize("N", [64, 256])
@@ -201,9 +241,22 @@ def test_golden_trajectory_teacher_forced(M, N):
         assert np.array_equal(gxa[t], d["xa"][t + 1])
     assert np.all(np.abs(r - d["reward"]) <= RTOL * np.abs(d["reward"]))
     assert not done.any().item()
-    # fused rasterise of (nearly) the golden states: positions exact, grids equal wherever no locust moved bins
+    # fused rasterise of (nearly) the golden states: agent cells exact (the agent update is FP64-exact); the grid is
+    # bit-exact for the DEVICE positions, and differs from the golden grid only where a locust sits within the FP32
+    # step error of a bin edge (a handful of cells at most, each by one count)
     grid, pos = env.grid.cpu().numpy(), env.positions.cpu().numpy()
     assert np.array_equal(pos, d["pos"][1:17])
+    moved = 0
+    for t in range(16):
+        g_dev, p_dev = so.rasterize(gx[t], gxa[t], 84)
+        assert np.array_equal(grid[t], g_dev.astype(np.float32)) and np.array_equal(pos[t], p_dev), t
+        ref = dense_grid(d["grid_idx_%d" % (t + 1)], d["grid_val_%d" % (t + 1)]).astype(np.float32)
+        assert np.array_equal(grid[t][..., 1], ref[..., 1]), t                     # agent channel: exact
+        diff = np.abs(grid[t][..., 0] - ref[..., 0])
+        assert diff.max() <= 1.0 / N + 1e-7                                         # one locust at most per cell
+        moved += int((diff > 0).sum())
+        assert abs(float(grid[t][..., 0].sum()) - float(ref[..., 0].sum())) <= 1.0 / N + 1e-6      # nobody lost
+    assert moved <= 8, moved
 
 
 # --------------------------------------------------------------------------------------- rasteriser
@@ -630,9 +683,9 @@ def test_follower_rasteriser_large_swarm_grid_sizes(M, G):
     nat = M.nat
     E, N = 37, 176
     a = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes",
-                          tuning=1 | nat.TUNE_RASTER_FOLLOW)
+                          tuning=nat.TUNE_RASTER_FOLLOW)
     b = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=9, max_episode_steps=3, binding="ctypes",
-                          tuning=1 | nat.TUNE_RASTER_WARPS)
+                          tuning=nat.TUNE_RASTER_WARPS)
     b.state_c.work, b.state_c.work_words = None, 0           # static assignment, no work queue
     a.reset(); b.reset()
     rs = np.random.RandomState(G)
@@ -650,39 +703,38 @@ def test_follower_rasteriser_large_swarm_grid_sizes(M, G):
     assert int(a.episode[0]) == 2
 
 
-@pytest.mark.parametrize("N", [40, 64, 128, 176, 256, 320, 512])
+@pytest.mark.parametrize("N", [40, 64, 80, 128, 176, 256, 320, 512, 700])
 def test_launch_shapes_bitwise_identical(M, N):
-    """swarm_step picks its launch shape by batch size: 1, 2 or 4 warps per 64-locust super-tile (the pair work of a
-    super-tile is cut into four canonical chunks summed in a fixed tree, whoever computes them) and one of three places
-    for the rasteriser (follower kernel, raster warps, the step's own threads).  Every combination must give the same
-    BITS -- a trajectory must not depend on how many envs share a GPU -- and agree with the oracle."""
+    """swarm_step picks its launch shape by batch size: the rasteriser runs in a follower kernel, in raster warps of the
+    step kernel or on the step's own threads (with the agents' pull evaluated before or after the tile passes, a filler
+    warp or plain stores for the zeros, programmatic dependent launch or not).  Every shape must give the same BITS -- a
+    trajectory must not depend on how many envs share a GPU -- and agree with the oracle."""
     nat = M.nat
     E = 21
     ref = None
     rs = np.random.RandomState(N)
     acts = [to_dev(clipped(rs, (E, 10, 2))) for _ in range(5)]
-    for ks in (1, 2, 4):
-        for place in (nat.TUNE_RASTER_WARPS, nat.TUNE_RASTER_SELF, nat.TUNE_RASTER_FOLLOW):
-            env = M.BatchedSwarmEnv(E, n_locusts=N, seed=77, max_episode_steps=3, tuning=ks | place)
-            env.reset()
-            v0, r0 = env.forces()
-            outs = [v0.clone(), r0.clone()]
-            for t in range(5):                          # crosses an auto-reset (limit 3) inside the step kernel
-                env.step(acts[t].clone())
-                outs += [env.x.clone(), env.xa.clone(), env.grid.clone(), env.positions.clone(), env.reward.clone(),
-                         env.done_u8.clone(), env.episode.clone(), env.elapsed.clone()]
-            torch.cuda.synchronize()
-            assert int(env.work.sum()) == 0
-            if ref is None:
-                ref = outs
-                x, xa = env.x.cpu().numpy(), env.xa.cpu().numpy()
-                for e in range(0, E, 5):
-                    g, p_ = so.rasterize(x[e], xa[e], 84)
-                    assert np.array_equal(env.grid[e].cpu().numpy(), g.astype(np.float32))
-                    assert np.array_equal(env.positions[e].cpu().numpy(), p_)
-            else:
-                for i, (a, b) in enumerate(zip(ref, outs)):
-                    assert torch.equal(a, b), (N, ks, place >> 4, i)
+    for place in (nat.TUNE_RASTER_WARPS, nat.TUNE_RASTER_SELF, nat.TUNE_RASTER_FOLLOW, 0):
+        env = M.BatchedSwarmEnv(E, n_locusts=N, seed=77, max_episode_steps=3, tuning=place)
+        env.reset()
+        v0, r0 = env.forces()
+        outs = [v0.clone(), r0.clone()]
+        for t in range(5):                          # crosses an auto-reset (limit 3) inside the step kernel
+            env.step(acts[t].clone())
+            outs += [env.x.clone(), env.xa.clone(), env.grid.clone(), env.positions.clone(), env.reward.clone(),
+                     env.done_u8.clone(), env.episode.clone(), env.elapsed.clone()]
+        torch.cuda.synchronize()
+        assert int(env.work.sum()) == 0
+        if ref is None:
+            ref = outs
+            x, xa = env.x.cpu().numpy(), env.xa.cpu().numpy()
+            for e in range(0, E, 5):
+                g, p_ = so.rasterize(x[e], xa[e], 84)
+                assert np.array_equal(env.grid[e].cpu().numpy(), g.astype(np.float32))
+                assert np.array_equal(env.positions[e].cpu().numpy(), p_)
+        else:
+            for i, (a, b) in enumerate(zip(ref, outs)):
+                assert torch.equal(a, b), (N, place >> 4, i)
 
 
 def test_add_wind_false_matches_reference_semantics(M):

@@ -25,9 +25,9 @@ def test_follower_stress_two_streams(M):
         G = rnd.choice([20, 83, 84])
         lim = rnd.choice([2, 5, 128])
         a = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=trial, max_episode_steps=lim, binding="ctypes",
-                              tuning=1 | nat.TUNE_RASTER_FOLLOW)
+                              tuning=nat.TUNE_RASTER_FOLLOW)
         b = M.BatchedSwarmEnv(E, n_locusts=N, grid_size=G, seed=trial, max_episode_steps=lim, binding="ctypes",
-                              tuning=rnd.choice([1, 2]) | rnd.choice([nat.TUNE_RASTER_WARPS, nat.TUNE_RASTER_SELF]))
+                              tuning=rnd.choice([nat.TUNE_RASTER_WARPS, nat.TUNE_RASTER_SELF]))
         a.reset(); b.reset()
         s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
         act = torch.randn(E, 10, 2, device="cuda").clamp(-0.9, 0.9)
@@ -48,8 +48,8 @@ def test_two_followers_on_two_streams_concurrently(M):
     side stream / events of ITS caller stream (VERDICT r01 weak #10), so neither can wait on the other's fork event."""
     nat = M.nat
     E, N = 600, 256
-    envs = [M.BatchedSwarmEnv(E, n_locusts=N, seed=5, max_episode_steps=4, tuning=1 | nat.TUNE_RASTER_FOLLOW) for _ in range(2)]
-    ref = M.BatchedSwarmEnv(E, n_locusts=N, seed=5, max_episode_steps=4, tuning=1 | nat.TUNE_RASTER_SELF)
+    envs = [M.BatchedSwarmEnv(E, n_locusts=N, seed=5, max_episode_steps=4, tuning=nat.TUNE_RASTER_FOLLOW) for _ in range(2)]
+    ref = M.BatchedSwarmEnv(E, n_locusts=N, seed=5, max_episode_steps=4, tuning=nat.TUNE_RASTER_SELF)
     for e in envs + [ref]:
         e.reset()
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
