@@ -226,6 +226,20 @@ class BatchedSwarmEnv(object):
             nat.check(rc, "swarm_step")
         return (self.x, self.xa), self.reward, self._done_view, {}
 
+    def stagger_episodes(self, total_envs=None):
+        """Opt-in de-synchronisation of the episode boundaries (NOT the reference's behaviour: there every emulator starts
+        at elapsed = 0 and all of them hit TimeLimit(128) on the same step, emulator_runner.py:126-132, so every 128th
+        batch-step carries the 10 burn-in steps of EVERY env).  Sets env e's TimeLimit counter to
+        (global_id * max_episode_steps) // total_envs: from then on E/128 envs end their episode on each step -- their
+        first episode is shorter, everything else is unchanged.  Call right after reset()."""
+        lim = int(self.params.max_episode_steps)
+        if lim <= 0:
+            raise ValueError("stagger_episodes needs a TimeLimit (max_episode_steps > 0)")
+        total = int(total_envs) if total_envs is not None else self.E
+        ids = torch.arange(self.E, device=self.device, dtype=torch.int64) + int(self.params.env_id_offset)
+        self.elapsed.copy_(((ids * lim) // max(total, 1) % lim).to(torch.int32))
+        return self.elapsed
+
     def plan(self, rasterize=None):
         """swarm_step_plan: the launch shape step() uses for this batch, as a dict."""
         io = nat.SwarmStepIO()

@@ -19,6 +19,7 @@ def main():
         if k in d:
             lines.append("| %s | %s | %s |" % (k, d[k][0], d[k][1]))
             vals[k] = d[k][0]
+            vals[k + "__unit"] = d[k][1]
     if mix:
         tot = sum(mix.values())
         lines += ["", "## executed warp-instruction mix (SASS opcode, share of %d)" % tot, "", "| opcode | warp instr | share |",

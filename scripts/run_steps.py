@@ -9,7 +9,11 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 12
 env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128)
 env.reset()
 a = torch.randn(E, 10, 2, device="cuda").clamp(-0.7, 0.7).contiguous()
+v = torch.empty(E, N, 2, dtype=torch.float32, device="cuda")
+r = torch.empty(E, dtype=torch.float32, device="cuda")
 for _ in range(steps):
     env.step(a)
+    env.forces(v=v, reward=r)
 torch.cuda.synchronize()
+print("plan", env.plan())
 print("ok", E, N, steps, float(env.reward.mean()))

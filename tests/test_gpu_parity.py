@@ -760,3 +760,23 @@ def test_add_wind_false_matches_reference_semantics(M):
     f.reset()
     st, rr, dd, _ = f._step(np.zeros((10, 2)), add_wind=False)
     assert rr < 0 and not dd
+
+
+def test_stagger_episodes_spreads_the_resets(M):
+    """BatchedSwarmEnv.stagger_episodes (opt-in; the reference keeps every emulator in lock-step): with E = 4 x limit envs
+    exactly 4 episodes end on every step, every env resets once per `limit` steps, and an env's trajectory within an
+    episode is the one the un-staggered batch produces from the same state (the stagger only moves the TimeLimit)."""
+    E, N, LIM = 64, 16, 16
+    env = M.BatchedSwarmEnv(E, n_locusts=N, seed=8, max_episode_steps=LIM)
+    env.reset()
+    el = env.stagger_episodes().cpu().numpy()
+    assert sorted(el.tolist()) == sorted([(e * LIM) // E for e in range(E)])
+    act = torch.zeros(E, 10, 2, device="cuda")
+    resets = np.zeros(E, dtype=int)
+    for t in range(2 * LIM):
+        _, _, done, _ = env.step(act)
+        d = done.cpu().numpy()
+        assert d.sum() == E // LIM, (t, d.sum())
+        resets += d
+    assert (resets == 2).all()
+    assert (env.episode.cpu().numpy() == 3).all()
