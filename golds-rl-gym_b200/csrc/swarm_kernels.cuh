@@ -116,7 +116,7 @@ __host__ __device__ inline size_t smem_table_bytes(int N, int A, int G) {
 // sym: 0 = ordered pairs (MODE 2/4), 1 = unordered, 32-wide tiles (MODE 1), 2 = unordered, 64-wide (MODE 3)
 __host__ __device__ inline int sym_tiles(int N, int sym) { return sym == 2 ? 2 * ((N + 63) >> 6) : n_tiles(N); }
 __host__ __device__ inline int sym_slots(int N, int sym) {
-    return sym == 2 ? 1 + ((N + 63) >> 6) / 2 : 1 + n_tiles(N) / 2;
+    return sym == 2 ? 1 + ((N + 63) >> 6) / 2 : 2 * (1 + n_tiles(N) / 2);      // MODE 1: two reaction streams per pass
 }
 __host__ __device__ inline size_t smem_slot_bytes(int N, int sym) {
     return sym ? smem_align(sizeof(float2) * sym_tiles(N, sym) * sym_slots(N, sym) * 32) : 0;
@@ -351,101 +351,7 @@ __device__ __forceinline__ void stage_locusts(const Smem& sm, const KP& kp, cons
 
 constexpr int kTileUnroll = 4;   // rotation steps unrolled together (x targets per lane = pair chains in flight)
 
-// n rotation steps of one tile pass.  tl points at the first element this lane meets (inside a
-// doubled tile, so tl[k] is element (first+k)%32 without wrap logic).  The own force accumulates
-// in (ax,ay); (bx,by) is the reaction on the met element and moves one lane down BEFORE every
-// step (also before the first one: it then carries zeros, or the caller's partial sum), so that
-// it follows its element.  On return lane l holds the reaction for the element met last.
-template <bool PRECISE>
-__device__ __forceinline__ void tile_sym(const float4* __restrict__ tl, const int n, const float4 tg, const KP& kp,
-                                         const int nxt, float& ax, float& ay, float& bx, float& by) {
-#pragma unroll kTileUnroll
-    for (int k = 0; k < n; ++k) {
-        bx = __shfl_sync(kFull, bx, nxt);
-        by = __shfl_sync(kFull, by, nxt);
-        const float4 q = tl[k];
-        const float dx = (q.x - tg.x) + (q.z - tg.z);
-        const float dy = (q.y - tg.y) + (q.w - tg.w);
-        const float w = pair_weight<PRECISE>(dx, dy, kp);
-        ax = fmaf(w, dx, ax);
-        ay = fmaf(w, dy, ay);
-        bx = fmaf(-w, dx, bx);
-        by = fmaf(-w, dy, by);
-    }
-}
-
-// MODE 1, part 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I
-// meets itself (lane offsets 1..15 with reaction, offset 16 one way: each such pair appears in two
-// lanes, offset 0 = self), tiles I+1..I+floor((nt-1)/2) fully and tile I+nt/2 (nt even) half each
-// way.  One loop over these passes, so the pair code exists once.  The reaction sums land in
-// sm.slot; the caller must barrier before forces_sym_finish.
-template <bool PRECISE, bool AGF>
-__device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
-    const int lane = g.tid & 31, I = g.tid >> 5;
-    const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
-    const int nxt = (lane + 1) & 31;
-    const int nfull = (nt - 1) >> 1;
-    const float4* S = sm.src;
-    const float4 tg = S[I * 64 + lane];
-    if constexpr (AGF) {   // the agents' pull on this lane's locust (multiagent.py:108-113), summed from 0, added last in the finish
-        const float4* ag = S + nt * 64;
-        float gx = 0.f, gy = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
-        sm.agf[I * 32 + lane] = make_float2(gx, gy);
-    }
-    ax = 0.f;
-    ay = 0.f;
-    pair_ordered<PRECISE>(S[I * 64 + lane + 16], tg, kp, ax, ay);
-#pragma unroll 1
-    for (int o = 0; o < nslots; ++o) {
-        int B = I, first = 1, n = 15;                    // own tile
-        if (o > 0) {
-            if (o <= nfull) {                            // a full tile pair
-                B = I + o;
-                if (B >= nt) B -= nt;
-                first = 0;
-                n = 32;
-            } else {   // lane offsets 0..15 from the lower tile, 16..31 (= 1..16 seen from the partner) from the upper
-                B = I < o ? I + o : I - o;
-                first = I < o ? 0 : 1;
-                n = 16;
-            }
-        }
-        float bx = 0.f, by = 0.f;
-        tile_sym<PRECISE>(S + B * 64 + lane + first, n, tg, kp, nxt, ax, ay, bx, by);
-        sm.slot[(B * nslots + o) * 32 + ((lane + first + n - 1) & 31)] = make_float2(bx, by);
-    }
-}
-
-// MODE 1, part 2: add the reactions (fixed order: bitwise reproducible) and the agents' pull.
-template <bool PRECISE, bool AGF>
-__device__ __forceinline__ void forces_sym_finish(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
-    const int lane = g.tid & 31, I = g.tid >> 5;
-    const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
-    for (int o = 0; o < nslots; ++o) {
-        const float2 r = sm.slot[(I * nslots + o) * 32 + lane];
-        ax += r.x;
-        ay += r.y;
-    }
-    // the agents' pull, summed from 0 and added last: either evaluated before the tile passes (AGF: the latency-bound
-    // shape, where this keeps it off the critical path behind the barrier) or here -- the same bits either way
-    if constexpr (AGF) {
-        const float2 a = sm.agf[I * 32 + lane];     // written by this very thread in forces_sym_tiles
-        ax += a.x;
-        ay += a.y;
-    } else {
-        const float4 tg = sm.src[I * 64 + lane];
-        const float4* ag = sm.src + nt * 64;
-        float gx = 0.f, gy = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
-        ax += gx;
-        ay += gy;
-    }
-}
-
-// ---- MODE 3: 64-wide super-tiles, two targets (A: first half, B: second half) per lane -------
+// one unordered pair: force of source q on target tg, and (REACT) its reaction on the source
 template <bool REACT, bool PRECISE>
 __device__ __forceinline__ void pair_sym(const float4 q, const float4 tg, const KP& kp, float& ax, float& ay,
                                          float& bx, float& by) {
@@ -459,6 +365,7 @@ __device__ __forceinline__ void pair_sym(const float4 q, const float4 tg, const 
         by = fmaf(-w, dy, by);
     }
 }
+
 
 // ---- packed FP32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): one issue slot, two FP32 results ------
 typedef unsigned long long f32x2;
@@ -484,6 +391,171 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
+
+// n2 rotation steps of one tile pass with TWO sources per step: the lane meets tl1[k] (stream 1) and tl2[k] (stream 2;
+// the same doubled tile, 8 or 16 elements further on, so tl[k] never needs wrap logic).  The own force accumulates in
+// (ax,ay) -- stream 1 first, then stream 2; (b1, b2) are the reactions on the two met elements and move one lane down
+// BEFORE every step (also before the first one: they then carry zeros, or the caller's partial sum), so that each follows
+// its element.  On return lane l holds the reactions for the two elements met last.  Fast math packs the two pairs into
+// FADD2 / FMUL2 / FFMA2 (geometry by component, the r -> w chain across the two sources); MUFU stays scalar.
+template <bool PRECISE>
+__device__ __forceinline__ void tile_sym_dual(const float4* __restrict__ tl1, const float4* __restrict__ tl2, const int n2,
+                                              const float4 tg, const KP& kp, const int nxt, float& ax, float& ay,
+                                              float& b1x, float& b1y, float& b2x, float& b2y) {
+    if constexpr (PRECISE) {
+#pragma unroll 2
+        for (int k = 0; k < n2; ++k) {
+            b1x = __shfl_sync(kFull, b1x, nxt); b1y = __shfl_sync(kFull, b1y, nxt);
+            b2x = __shfl_sync(kFull, b2x, nxt); b2y = __shfl_sync(kFull, b2y, nxt);
+            const float4 q1 = tl1[k], q2 = tl2[k];
+            {
+                const float dx = (q1.x - tg.x) + (q1.z - tg.z), dy = (q1.y - tg.y) + (q1.w - tg.w);
+                const float w = pair_weight<PRECISE>(dx, dy, kp);
+                ax = fmaf(w, dx, ax); ay = fmaf(w, dy, ay);
+                b1x = fmaf(-w, dx, b1x); b1y = fmaf(-w, dy, b1y);
+            }
+            {
+                const float dx = (q2.x - tg.x) + (q2.z - tg.z), dy = (q2.y - tg.y) + (q2.w - tg.w);
+                const float w = pair_weight<PRECISE>(dx, dy, kp);
+                ax = fmaf(w, dx, ax); ay = fmaf(w, dy, ay);
+                b2x = fmaf(-w, dx, b2x); b2y = fmaf(-w, dy, b2y);
+            }
+        }
+    } else {
+        const f32x2 nh = pk2(-tg.x, -tg.y), nl = pk2(-tg.z, -tg.w);
+        const f32x2 nInvL2 = pk2(kp.nInvL, kp.nInvL), nF2 = pk2(-kp.F, -kp.F), eps2 = pk2(kp.eps_s, kp.eps_s);
+        f32x2 na = pk2(-ax, -ay);
+#pragma unroll kTileUnroll
+        for (int k = 0; k < n2; ++k) {
+            b1x = __shfl_sync(kFull, b1x, nxt); b1y = __shfl_sync(kFull, b1y, nxt);
+            b2x = __shfl_sync(kFull, b2x, nxt); b2y = __shfl_sync(kFull, b2y, nxt);
+            const float4 q1 = tl1[k], q2 = tl2[k];
+            const f32x2 d1 = add2(add2(pk2(q1.x, q1.y), nh), add2(pk2(q1.z, q1.w), nl));
+            const f32x2 d2 = add2(add2(pk2(q2.x, q2.y), nh), add2(pk2(q2.z, q2.w), nl));
+            float d1x, d1y, d2x, d2y;
+            upk2(d1, d1x, d1y);
+            upk2(d2, d2x, d2y);
+            // r2 >= 1e-30 keeps rsqrt finite for coincident points (their d is 0 anyway)
+            const float r2a = fmaf(d1x, d1x, fmaf(d1y, d1y, 1e-30f));
+            const float r2b = fmaf(d2x, d2x, fmaf(d2y, d2y, 1e-30f));
+            float ria, rib;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ria) : "f"(r2a));
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rib) : "f"(r2b));
+            const f32x2 r = mul2(pk2(r2a, r2b), pk2(ria, rib));
+            const f32x2 arg = mul2(r, nInvL2);
+            const f32x2 rpe = add2(r, eps2);
+            float ra, rb, ga, gb, pa, pb;
+            upk2(r, ra, rb);
+            upk2(arg, ga, gb);
+            upk2(rpe, pa, pb);
+            float e1a, e1b, e2a, e2b, ia, ib;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1a) : "f"(-ra));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1b) : "f"(-rb));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2a) : "f"(ga));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2b) : "f"(gb));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ia) : "f"(pa));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ib) : "f"(pb));
+            const f32x2 ns = fma2(nF2, pk2(e2a, e2b), pk2(e1a, e1b));      // -(F e2 - e1)
+            const f32x2 nw = mul2(ns, pk2(ia, ib));                        // (-w_1, -w_2)
+            float nwa, nwb;
+            upk2(nw, nwa, nwb);
+            const f32x2 nwa2 = pk2(nwa, nwa), nwb2 = pk2(nwb, nwb);
+            na = fma2(nwa2, d1, na);
+            na = fma2(nwb2, d2, na);
+            f32x2 b1 = fma2(nwa2, d1, pk2(b1x, b1y)), b2 = fma2(nwb2, d2, pk2(b2x, b2y));
+            upk2(b1, b1x, b1y);
+            upk2(b2, b2x, b2y);
+        }
+        upk2(na, ax, ay);
+        ax = -ax; ay = -ay;
+    }
+}
+
+// MODE 1, part 1: all locust-locust pairs once.  Thread = locust j (tile I = warp, lane).  Tile I
+// meets itself (lane offsets 1..15 with reaction, offset 16 one way: each such pair appears in two
+// lanes, offset 0 = self), tiles I+1..I+floor((nt-1)/2) fully and tile I+nt/2 (nt even) half each
+// way.  Every pass walks its offsets as TWO streams, half a pass apart (tile_sym_dual): 16 + 16 offsets of a full
+// tile, 8 + 8 of a half tile, and in the own tile 1..7 next to 9..15 with offset 8 taken first by stream 2 alone.
+// One loop over the passes, so the pair code exists once.  The two reaction sums of a pass land in sm.slot; the
+// caller must barrier before forces_sym_finish.
+template <bool PRECISE, bool AGF>
+__device__ __forceinline__ void forces_sym_tiles(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
+    const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
+    const int nxt = (lane + 1) & 31;
+    const int nfull = (nt - 1) >> 1;
+    const float4* S = sm.src;
+    const float4 tg = S[I * 64 + lane];
+    if constexpr (AGF) {   // the agents' pull on this lane's locust (multiagent.py:108-113), summed from 0, added last in the finish
+        const float4* ag = S + nt * 64;
+        float gx = 0.f, gy = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
+        sm.agf[I * 32 + lane] = make_float2(gx, gy);
+    }
+    ax = 0.f;
+    ay = 0.f;
+    pair_ordered<PRECISE>(S[I * 64 + lane + 16], tg, kp, ax, ay);
+#pragma unroll 1
+    for (int o = 0; o < nslots; ++o) {
+        int B = I, first = 1, n2 = 7, gap = 8;           // own tile: offsets 1..7 | 9..15 (8 below)
+        if (o > 0) {
+            if (o <= nfull) {                            // a full tile pair: offsets 0..15 | 16..31
+                B = I + o;
+                if (B >= nt) B -= nt;
+                first = 0;
+                n2 = 16;
+                gap = 16;
+            } else {   // lane offsets 0..15 from the lower tile, 16..31 (= 1..16 seen from the partner) from the upper
+                B = I < o ? I + o : I - o;
+                first = I < o ? 0 : 1;
+                n2 = 8;
+                gap = 8;
+            }
+        }
+        const float4* tl = S + B * 64 + lane + first;
+        float b1x = 0.f, b1y = 0.f, b2x = 0.f, b2y = 0.f;
+        if (o == 0) {     // own tile, offset 8: stream 2's first element (lanes are whole here: b2 is still zero everywhere)
+            pair_sym<true, PRECISE>(tl[7], tg, kp, ax, ay, b2x, b2y);
+        }
+        tile_sym_dual<PRECISE>(tl, tl + gap, n2, tg, kp, nxt, ax, ay, b1x, b1y, b2x, b2y);
+        float2* sl = sm.slot + (size_t)((B * nslots + o) * 2) * 32;
+        sl[(lane + first + n2 - 1) & 31] = make_float2(b1x, b1y);
+        sl[32 + ((lane + first + gap + n2 - 1) & 31)] = make_float2(b2x, b2y);
+    }
+}
+
+// MODE 1, part 2: add the reactions (fixed order: bitwise reproducible) and the agents' pull.
+template <bool PRECISE, bool AGF>
+__device__ __forceinline__ void forces_sym_finish(const Smem& sm, const KP& kp, const Grp& g, float& ax, float& ay) {
+    const int lane = g.tid & 31, I = g.tid >> 5;
+    const int nt = n_tiles(kp.N), nslots = 1 + nt / 2;
+    for (int o = 0; o < nslots; ++o) {
+        const float2* sl = sm.slot + (size_t)((I * nslots + o) * 2) * 32;
+        const float2 r1 = sl[lane], r2 = sl[32 + lane];
+        ax += r1.x;
+        ay += r1.y;
+        ax += r2.x;
+        ay += r2.y;
+    }
+    // the agents' pull, summed from 0 and added last: either evaluated before the tile passes (AGF: the latency-bound
+    // shape, where this keeps it off the critical path behind the barrier) or here -- the same bits either way
+    if constexpr (AGF) {
+        const float2 a = sm.agf[I * 32 + lane];     // written by this very thread in forces_sym_tiles
+        ax += a.x;
+        ay += a.y;
+    } else {
+        const float4 tg = sm.src[I * 64 + lane];
+        const float4* ag = sm.src + nt * 64;
+        float gx = 0.f, gy = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < kp.A; ++k) pair_ordered<PRECISE>(ag[k], tg, kp, gx, gy);
+        ax += gx;
+        ay += gy;
+    }
+}
+
+// ---- MODE 3: 64-wide super-tiles, two targets (A: first half, B: second half) per lane -------
 // Two targets of one lane, negated and split like the sources: d = (q.hi + nh) + (q.lo + nl).
 struct Targets2 {
     f32x2 nhA, nlA, nhB, nlB;
