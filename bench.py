@@ -196,7 +196,7 @@ def run_reference(args, wl):
     }))
 
 
-def paac_frames_per_sec(E_total, updates, warmup_updates, world, rank, local, seconds_cap=None):
+def paac_frames_per_sec(E_total, updates, warmup_updates, world, rank, local, seconds_cap=None, net_precision="fp32"):
     """PAAC frames/s (= T*E / loop time, paac.py:397-401) of the device-resident learner, CUDA-event timed.
     E_total emulators are sharded over the ranks.  seconds_cap bounds the timed region (updates are reduced, never
     below 50, and the figure says how many ran)."""
@@ -206,7 +206,7 @@ def paac_frames_per_sec(E_total, updates, warmup_updates, world, rank, local, se
     import train_paac_conv as tp
     args = tp.get_arg_parser().parse_args(["--height=84", "--clip_norm=1", "-ec", str(E_total)])
     net_creator, env_creator = tp.get_network_and_environment_creator(args)
-    learner = pkg.submodule("agents.paac.paac").GridPAACLearner(net_creator, env_creator, args, net_precision="fp32")
+    learner = pkg.submodule("agents.paac.paac").GridPAACLearner(net_creator, env_creator, args, net_precision=net_precision)
     learner.start()
     sh = pkg.submodule("sharding")
     dev = torch.device("cuda", local)
@@ -234,13 +234,18 @@ def paac_frames_per_sec(E_total, updates, warmup_updates, world, rank, local, se
     torch.cuda.synchronize()
     ms = sh.max_over_ranks(e0.elapsed_time(e1), device=dev)
     frames = updates * learner.max_local_steps * learner.total_emulators
-    return dict(frames_per_sec=frames / (ms * 1e-3), ms_per_update=ms / updates, updates=updates,
+    net_dtype = {"fp32": "fp32 (cuDNN / cuBLAS TF32 disabled: torch.backends.cudnn.allow_tf32 = cuda.matmul.allow_tf32 = False)",
+                 "tf32": "tf32 (EXTRA, not the reference's precision: TF32 tensor cores for convolutions and matmuls)",
+                 "bf16": "bf16 autocast (EXTRA, not the reference's precision)"}[net_precision]
+    res = dict(frames_per_sec=frames / (ms * 1e-3), ms_per_update=ms / updates, updates=updates,
                 emulators=learner.total_emulators, emulators_per_gpu=learner.emulator_counts,
                 local_steps=learner.max_local_steps, policy_batch=learner.real_batch_size,
                 observation="compact (grid + positions; conv1 factorised over the shared channels)" if learner.compact_obs
-                else "expanded (E,A,84,84,3)",
-                net_dtype="fp32 (cuDNN / cuBLAS TF32 disabled: torch.backends.cudnn.allow_tf32 = cuda.matmul.allow_tf32 = False)",
+                else "expanded (E,A,84,84,3)", net_dtype=net_dtype,
                 launch="one CUDA graph per update (rollout + returns + backward + all-reduce + Adam)")
+    del learner
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_paac(args, wl, key):
@@ -475,6 +480,8 @@ def main():
         try:
             paac = paac_frames_per_sec(PAAC["paac3"]["E"], 500, 20, 1, 0, local)
             paac["config"] = PAAC["paac3"]["name"]
+            extra = paac_frames_per_sec(PAAC["paac3"]["E"], 500, 20, 1, 0, local, net_precision="tf32")
+            paac["extra_tf32"] = {k: extra[k] for k in ("frames_per_sec", "ms_per_update", "updates", "net_dtype")}
         except Exception as exc:      # the secondary figure must never take the headline down
             paac = {"error": repr(exc)}
     paac5 = None
@@ -482,6 +489,8 @@ def main():
         try:
             paac5 = paac_frames_per_sec(PAAC["paac5"]["E"], 500, 5, world, rank, local, seconds_cap=40.0)
             paac5["config"] = PAAC["paac5"]["name"]
+            extra = paac_frames_per_sec(PAAC["paac5"]["E"], 200, 5, world, rank, local, seconds_cap=15.0, net_precision="tf32")
+            paac5["extra_tf32"] = {k: extra[k] for k in ("frames_per_sec", "ms_per_update", "updates", "net_dtype")}
         except Exception as exc:
             paac5 = {"error": repr(exc)}
 
