@@ -509,6 +509,33 @@ def main():
                                                     "roofline", "roofline_hbm", "cpu_baseline", "launch_shape") if k in d}
             except Exception as exc:
                 secondary[key] = {"error": repr(exc)}
+    # BASELINE.json configs[0] (C1): the single-env gym facade (numpy in / numpy out, one host round trip per step) next to
+    # the reference's own single-process rate on this box's CPU
+    if world == 1 and rank == 0 and args.workload == "c4" and not args.no_secondary:
+        try:
+            import numpy as np
+            fenv = M.make("Swarm-eval-v0")
+            fenv.reset()
+            rs = np.random.RandomState(0)
+            acts = rs.normal(size=(400, 10, 2)) * 0.5
+            for t in range(50):
+                fenv.step(acts[t])
+            t0 = time.perf_counter()
+            for t in range(50, 350):
+                _, _, dn, _ = fenv.step(acts[t])
+                if dn:
+                    fenv.reset()
+            c1 = {"facade_steps_per_sec": 300.0 / (time.perf_counter() - t0),
+                  "config": "C1: SwarmEnv (N=80, seed 192, TimeLimit 128) through the numpy-in / numpy-out gym facade, 300 steps incl. "
+                            "two resets; one kernel launch + host round trip per step"}
+            if not args.no_cpu_baseline:
+                from oracle import cpu_baseline as cb
+                if cb.reference_staged():
+                    r1 = cb.time_reference(80, steps=200, warmup=2, envs_per_proc=1, procs=1)
+                    c1["reference_steps_per_sec_one_process"] = r1["env_steps_per_s"]
+            secondary = dict(secondary or {}, c1=c1)
+        except Exception as exc:
+            secondary = dict(secondary or {}, c1={"error": repr(exc)})
     if weak is not None:
         secondary = dict(secondary or {}, weak=weak)
     if paac5 is not None:

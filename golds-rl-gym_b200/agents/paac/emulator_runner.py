@@ -39,10 +39,11 @@ class SwarmRunner(object):
         p = nat.SwarmParams(n_envs=E, n_locusts=1, n_agents=A, grid_size=G, n_burn_in=0, max_episode_steps=0,
                             math_mode=0, tuning=0, noise=0, gravity=0, wind=0, F=0, L=1, dt=0, box_width=3.0,
                             box_height=3.0, seed=0, env_id_offset=0)
-        nat.check(lib.swarm_expand_obs(ctypes.byref(p), ctypes.c_void_p(state.data_ptr()),
-                                       ctypes.c_void_p(agent_positions.data_ptr()), ctypes.c_void_p(out.data_ptr()),
-                                       ctypes.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)),
-                  "swarm_expand_obs")
+        with torch.cuda.device(state.device):      # the C side launches on the CURRENT device
+            nat.check(lib.swarm_expand_obs(ctypes.byref(p), ctypes.c_void_p(state.data_ptr()),
+                                           ctypes.c_void_p(agent_positions.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                           ctypes.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)),
+                      "swarm_expand_obs")
         return out[0] if single else out
 
     @staticmethod
@@ -52,8 +53,9 @@ class SwarmRunner(object):
         lib = nat.load()
         if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.shape[-1] != 2:
             raise ValueError("actions must be a contiguous float32 (...,2) CUDA tensor")
-        nat.check(lib.swarm_clip_actions(ctypes.c_void_p(actions.data_ptr()), actions.numel() // 2,
-                                         float(SwarmRunner.MAX_MOVE_NORM),
-                                         ctypes.c_void_p(torch.cuda.current_stream(actions.device).cuda_stream)),
-                  "swarm_clip_actions")
+        with torch.cuda.device(actions.device):    # the C side launches on the CURRENT device
+            nat.check(lib.swarm_clip_actions(ctypes.c_void_p(actions.data_ptr()), actions.numel() // 2,
+                                             float(SwarmRunner.MAX_MOVE_NORM),
+                                             ctypes.c_void_p(torch.cuda.current_stream(actions.device).cuda_stream)),
+                      "swarm_clip_actions")
         return actions

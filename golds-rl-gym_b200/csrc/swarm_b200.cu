@@ -186,8 +186,8 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             double2* oa = reinterpret_cast<double2*>(st.xa) + (size_t)e * A;
             double2* rx = sm.rx;
             const Stage stg = sm.st;
-            // the write-back of the new state: by everybody, or -- when this group rasterises its own env -- inside
-            // env_raster by the warps that are not walking the mean
+            // the write-back of the new state: by everybody here, or -- when this group rasterises its own env -- as
+            // the first thing inside env_raster
             auto write_back = [&](const int tid, const int n) {
                 for (int i = tid; i < N; i += n) {
                     const double2 q = stg.xs[i];
@@ -215,7 +215,7 @@ __global__ void __maxnreg__(64) k_step(const KP kp, const SwarmState st, const S
             if constexpr (self_raster) {
                 // state_processors.py:29-42 of the new state, straight from the stage buffer: [xs | as] are contiguous
                 // = vstack([x, xa]), final and visible since env_step's closing barrier
-                env_raster<true>(sm, stg.xs, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, filler,
+                env_raster<false>(sm, stg.xs, kp, g, io.grid + (size_t)e * cells * 2, io.positions + (size_t)e * A * 2, filler,
                                  ZeroSelf{filler, n_all}, NoRelease(), write_back, it == 0 ? (long long)blockIdx.x : -1);
                 if (filler && e1 < kp.E) bar_arrive<BAR_FULL>(n_all);   // clean again: the next env's zero fill may start
             }
@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(128) k_raster_follow(const KP kp, const double
     }
 }
 
-// SwarmStateProcessor.process_state for the batch (standalone: one CTA per env).
+// SwarmStateProcessor.process_state for the batch (standalone: one CTA per env).  EXACT: the caller wants the bounding
+// box (_get_bounding_box), so numpy's sequential mean is always walked; otherwise the same verified parallel mean as the step.
+template <bool EXACT>
 __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __restrict__ x,
                                                    const double* __restrict__ xa, float* __restrict__ grid,
                                                    uint8_t* __restrict__ positions, double* __restrict__ box) {
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__(256) k_rasterize(const KP kp, const double* __
     raster_table_clear(sm, (int)(smem_table_bytes(kp.N, kp.A, kp.G) / 4), g);
     raster_lut_fill(sm, kp, g.tid, g.n);
     g.sync();
-    env_raster<false>(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, ZeroOwn{false, 0}, NoRelease(), NoOverlap());
-    if (box && g.tid == 0) {
+    env_raster<EXACT>(sm, pts, kp, g, grid_e, positions + (size_t)e * kp.A * 2, false, ZeroOwn{false, 0}, NoRelease(), NoOverlap());
+    if (EXACT && box && g.tid == 0) {
         const double m = sm.box[0];
         box[4 * e + 0] = m - kp.half_w;
         box[4 * e + 1] = m + kp.half_w;
@@ -574,6 +576,7 @@ KP make_kp(const SwarmParams* p, int mode = 0) {
     k.nInvL = (float)(-1.0 / p->L);
     k.U = (float)p->wind; k.Gv = (float)p->gravity;
     k.eps_s = (float)(1e-6 * 1.4426950408889634);  // multiagent.py:103 "+ 0.000001", scaled
+    k.ri_max = 0.000244140625f / k.eps_s;          // eps / r <= 2^-12 (inv_r_eps)
     k.key = make_uint2((uint32_t)(p->seed & 0xffffffffu), (uint32_t)(p->seed >> 32));
     k.env_off = (uint32_t)p->env_id_offset;
     k.dynamic = 0;
@@ -1205,8 +1208,13 @@ int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa, flo
     const KP kp = make_kp(p);
     const size_t smem = smem_bytes(kp.N, kp.A, kp.G, 0, false, 1, 0);
     const int nt = (kp.N + kp.A) <= 128 ? 64 : 128;
-    if ((rc = prep(k_rasterize, smem))) return rc;
-    k_rasterize<<<kp.E, nt, smem, (cudaStream_t)stream>>>(kp, x, xa, grid, positions, box);
+    if (box) {
+        if ((rc = prep(k_rasterize<true>, smem))) return rc;
+        k_rasterize<true><<<kp.E, nt, smem, (cudaStream_t)stream>>>(kp, x, xa, grid, positions, box);
+    } else {
+        if ((rc = prep(k_rasterize<false>, smem))) return rc;
+        k_rasterize<false><<<kp.E, nt, smem, (cudaStream_t)stream>>>(kp, x, xa, grid, positions, box);
+    }
     return check_launch("swarm_rasterize");
 }
 

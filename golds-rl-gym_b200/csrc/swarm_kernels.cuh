@@ -44,6 +44,7 @@ struct KP {
     int E, N, A, G, n_burn, max_steps;
     double sigma, wind, dt, half_w, y_hi, cscale;
     float F, nInvL, U, Gv, eps_s;
+    float ri_max;     // 2^-12 / eps_s: pairs with 1/r above it (closer than 4096 eps) take MUFU.RCP for 1/(r + eps), see inv_r_eps
     uint2 key;
     uint32_t env_off;
     int dynamic;      // k_step: draw the third and later envs of a CTA from the work queue (SwarmState::work)
@@ -93,6 +94,7 @@ struct Smem {
                       // when the counts do not fit
     int* cid;         // N+A: cell written out by this point (or -1); before that, the point's y bin count
     float* lut;       // kLutL + kLutA: grid values count / N (locusts) and count / A (agents) of the small counts
+    double* rred;     // 2 kMaxWarps + 2: per-warp (sum x, max |x|) of the parallel mean; then the "some point is next to an edge" flag
 };
 
 __host__ __device__ inline size_t smem_align(size_t v) { return (v + 15) & ~size_t(15); }
@@ -128,6 +130,7 @@ __host__ __device__ inline size_t smem_agf_bytes(int N, int sym) {
 __host__ __device__ inline size_t smem_force_bytes(int N, int A, int sym, bool agf) {
     return smem_src_bytes(N, A, sym) + smem_slot_bytes(N, sym) + (agf ? smem_agf_bytes(N, sym) : 0);
 }
+constexpr int kMaxWarps = 32;             // threads of a rasterising group / 32, at most
 constexpr int kLutL = 256, kLutA = 33;     // grid-value look-up: counts below kLutL locusts / kLutA agents per cell
 __host__ __device__ inline int lut_locusts(int N) { return N + 1 < kLutL ? N + 1 : kLutL; }
 __host__ __device__ inline int lut_agents(int A) { return A + 1 < kLutA ? A + 1 : kLutA; }
@@ -135,7 +138,8 @@ __host__ __device__ inline int lut_agents(int A) { return A + 1 < kLutA ? A + 1 
 __host__ __device__ inline size_t smem_raster_bytes(int N, int A, int G, int raster) {
     if (!raster) return 0;
     return (raster == 1 ? smem_align(sizeof(double2) * (N + A)) : 0) + smem_table_bytes(N, A, G) +
-           smem_align(sizeof(int) * (N + A)) + smem_align(sizeof(float) * (lut_locusts(N) + lut_agents(A)));
+           smem_align(sizeof(int) * (N + A)) + smem_align(sizeof(float) * (lut_locusts(N) + lut_agents(A))) +
+           smem_align(sizeof(double) * (2 * kMaxWarps + 2));
 }
 // n_stage: stage buffers (2 in the pipelined step kernel, 1 in reset/forces, 0 in the rasteriser)
 __host__ __device__ inline size_t smem_bytes(int N, int A, int G, int n_stage, bool force, int raster, int sym) {
@@ -172,7 +176,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int N, int A, int G, 
     if (raster == 1) o += smem_align(sizeof(double2) * (N + A));
     s.table = reinterpret_cast<uint32_t*>(base + o); o += smem_table_bytes(N, A, G);
     s.cid = reinterpret_cast<int*>(base + o);       o += smem_align(sizeof(int) * (N + A));
-    s.lut = reinterpret_cast<float*>(base + o);
+    s.lut = reinterpret_cast<float*>(base + o);     o += smem_align(sizeof(float) * (lut_locusts(N) + lut_agents(A)));
+    s.rred = reinterpret_cast<double*>(base + o);
     return s;
 }
 
@@ -273,6 +278,25 @@ __device__ __forceinline__ double div_by_const(const double a, const double b, c
 // carries ~2^-24 RELATIVE error however close the two particles are (plain FP32 positions lose
 // the direction of close pairs, where s/(r+eps) is steepest).  Coincident points (and the self
 // pair of the ordered loop) have d = 0 exactly and contribute exactly 0.
+// 1 / (r + eps) from rinv ~ 1/r without a third trip to the XU pipe (the pipe that bounds the pair loop):
+//   1/(r + eps) = rinv / (1 + eps rinv) = rinv - (eps rinv) rinv + O((eps/r)^2),
+// one FMUL + one FFMA.  The dropped term is below 2^-24 -- the rounding of the result -- when eps rinv <= 2^-12, i.e. for
+// every pair further apart than 4096 eps (0.004 in the reference's units); closer pairs (a handful per reset, and the
+// ordered modes' self pair) take MUFU.RCP as before.  The choice depends on the pair alone, so every tiling and launch
+// shape still produces the same bits.
+#ifndef SWARM_RCP_SERIES
+#define SWARM_RCP_SERIES 1
+#endif
+__device__ __forceinline__ float inv_r_eps(const float r, const float rinv, const float eps_s, const float ri_max) {
+    float inv;
+#if SWARM_RCP_SERIES
+    inv = fmaf(-eps_s * rinv, rinv, rinv);
+    if (rinv > ri_max)
+#endif
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + eps_s));
+    return inv;
+}
+
 template <bool PRECISE>
 __device__ __forceinline__ float pair_weight(const float dx, const float dy, const KP& kp) {
     if (PRECISE) {
@@ -288,7 +312,7 @@ __device__ __forceinline__ float pair_weight(const float dx, const float dy, con
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-r));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(r * kp.nInvL));
         const float s = fmaf(kp.F, e2, -e1);
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + kp.eps_s));
+        inv = inv_r_eps(r, rinv, kp.eps_s, kp.ri_max);
         return s * inv;
     }
 }
@@ -337,9 +361,9 @@ __device__ __forceinline__ void stage_locusts(const Smem& sm, const KP& kp, cons
     if (ModeT<MODE>::SYM) {
         const int nt = sym_tiles(N, ModeT<MODE>::SYM);
         // pad lanes sit far away: as sources they contribute exactly 0 (both exponentials underflow)
-        const float4 pad = make_float4(1e15f, 0.f, 0.f, 0.f);
+        // (and 1e12 from one another: a pad-pad pair must not look like a close pair to inv_r_eps)
         for (int j = g.tid; j < nt * 32; j += g.n) {
-            const float4 q = j < N ? split_hilo(sm.st.xs[j], kp.cscale) : pad;
+            const float4 q = j < N ? split_hilo(sm.st.xs[j], kp.cscale) : make_float4(1e15f + 1e12f * (float)(j - N), 0.f, 0.f, 0.f);
             float4* t = sm.src + (j >> 5) * 64 + (j & 31);
             t[0] = q;
             t[32] = q;
@@ -391,6 +415,45 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
+struct PairConst2 {
+    f32x2 nInvL2, nF2, neps2;
+    float ri_max;
+};
+__device__ __forceinline__ PairConst2 make_pair_const2(const KP& kp) {
+    PairConst2 c;
+    c.nInvL2 = pk2(kp.nInvL, kp.nInvL);
+    c.nF2 = pk2(-kp.F, -kp.F);
+    c.neps2 = pk2(-kp.eps_s, -kp.eps_s);
+    c.ri_max = kp.ri_max;
+    return c;
+}
+
+// inv_r_eps for two pairs at once: the same roundings, packed; the close-pair test is one FMNMX + FSETP for both.
+__device__ __forceinline__ f32x2 inv_r_eps2(const f32x2 r, const float riA, const float riB, const PairConst2& c) {
+#if SWARM_RCP_SERIES
+    const f32x2 ri = pk2(riA, riB);
+    f32x2 inv = fma2(mul2(c.neps2, ri), ri, ri);
+    if (fmaxf(riA, riB) > c.ri_max) {
+        float rA, rB, iA, iB, ne, ne_;
+        upk2(r, rA, rB);
+        upk2(inv, iA, iB);
+        upk2(c.neps2, ne, ne_);
+        if (riA > c.ri_max) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(rA - ne));
+        if (riB > c.ri_max) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iB) : "f"(rB - ne));
+        inv = pk2(iA, iB);
+    }
+    return inv;
+#else
+    float pA, pB, iA, iB, ne, ne_;
+    upk2(r, pA, pB);
+    upk2(c.neps2, ne, ne_);
+    pA -= ne; pB -= ne;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(pA));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iB) : "f"(pB));
+    return pk2(iA, iB);
+#endif
+}
+
 
 // n2 rotation steps of one tile pass with TWO sources per step: the lane meets tl1[k] (stream 1) and tl2[k] (stream 2;
 // the same doubled tile, 8 or 16 elements further on, so tl[k] never needs wrap logic).  The own force accumulates in
@@ -423,7 +486,7 @@ __device__ __forceinline__ void tile_sym_dual(const float4* __restrict__ tl1, co
         }
     } else {
         const f32x2 nh = pk2(-tg.x, -tg.y), nl = pk2(-tg.z, -tg.w);
-        const f32x2 nInvL2 = pk2(kp.nInvL, kp.nInvL), nF2 = pk2(-kp.F, -kp.F), eps2 = pk2(kp.eps_s, kp.eps_s);
+        const PairConst2 c = make_pair_const2(kp);
         f32x2 na = pk2(-ax, -ay);
 #pragma unroll kTileUnroll
         for (int k = 0; k < n2; ++k) {
@@ -442,21 +505,17 @@ __device__ __forceinline__ void tile_sym_dual(const float4* __restrict__ tl1, co
             asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ria) : "f"(r2a));
             asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rib) : "f"(r2b));
             const f32x2 r = mul2(pk2(r2a, r2b), pk2(ria, rib));
-            const f32x2 arg = mul2(r, nInvL2);
-            const f32x2 rpe = add2(r, eps2);
-            float ra, rb, ga, gb, pa, pb;
+            const f32x2 arg = mul2(r, c.nInvL2);
+            float ra, rb, ga, gb;
             upk2(r, ra, rb);
             upk2(arg, ga, gb);
-            upk2(rpe, pa, pb);
-            float e1a, e1b, e2a, e2b, ia, ib;
+            float e1a, e1b, e2a, e2b;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1a) : "f"(-ra));
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1b) : "f"(-rb));
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2a) : "f"(ga));
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2b) : "f"(gb));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ia) : "f"(pa));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ib) : "f"(pb));
-            const f32x2 ns = fma2(nF2, pk2(e2a, e2b), pk2(e1a, e1b));      // -(F e2 - e1)
-            const f32x2 nw = mul2(ns, pk2(ia, ib));                        // (-w_1, -w_2)
+            const f32x2 ns = fma2(c.nF2, pk2(e2a, e2b), pk2(e1a, e1b));    // -(F e2 - e1)
+            const f32x2 nw = mul2(ns, inv_r_eps2(r, ria, rib, c));         // (-w_1, -w_2)
             float nwa, nwb;
             upk2(nw, nwa, nwb);
             const f32x2 nwa2 = pk2(nwa, nwa), nwb2 = pk2(nwb, nwb);
@@ -566,17 +625,6 @@ __device__ __forceinline__ Targets2 make_targets2(const float4 tgA, const float4
     t.nhB = pk2(-tgB.x, -tgB.y); t.nlB = pk2(-tgB.z, -tgB.w);
     return t;
 }
-struct PairConst2 {
-    f32x2 nInvL2, nF2, eps2;
-};
-__device__ __forceinline__ PairConst2 make_pair_const2(const KP& kp) {
-    PairConst2 c;
-    c.nInvL2 = pk2(kp.nInvL, kp.nInvL);
-    c.nF2 = pk2(-kp.F, -kp.F);
-    c.eps2 = pk2(kp.eps_s, kp.eps_s);
-    return c;
-}
-
 // One source q against both targets of the lane, fast math.  The geometry is packed by component
 // (x,y), the scalar chain r -> w by target (A,B); MUFU stays scalar.  Accumulates the NEGATED
 // forces: naX += -w_X d_X (X = A, B) and, with REACT, the reaction b += -(w_A d_A + w_B d_B).
@@ -598,20 +646,16 @@ __device__ __forceinline__ void pair2_fast(const float4 q, const Targets2& t, co
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(riB) : "f"(r2B));
     const f32x2 r = mul2(pk2(r2A, r2B), pk2(riA, riB));
     const f32x2 arg = mul2(r, c.nInvL2);
-    const f32x2 rpe = add2(r, c.eps2);
-    float rA, rB, gA, gB, pA, pB;
+    float rA, rB, gA, gB;
     upk2(r, rA, rB);
     upk2(arg, gA, gB);
-    upk2(rpe, pA, pB);
-    float e1A, e1B, e2A, e2B, iA, iB;
+    float e1A, e1B, e2A, e2B;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1A) : "f"(-rA));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1B) : "f"(-rB));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2A) : "f"(gA));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2B) : "f"(gB));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(pA));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iB) : "f"(pB));
     const f32x2 ns = fma2(c.nF2, pk2(e2A, e2B), pk2(e1A, e1B));      // -(F e2 - e1)
-    const f32x2 nw = mul2(ns, pk2(iA, iB));                          // (-w_A, -w_B)
+    const f32x2 nw = mul2(ns, inv_r_eps2(r, riA, riB, c));           // (-w_A, -w_B)
     float nwA, nwB;
     upk2(nw, nwA, nwB);
     const f32x2 nwA2 = pk2(nwA, nwA), nwB2 = pk2(nwB, nwB);
@@ -1064,14 +1108,32 @@ struct ZeroSelf {            // filler: the warp outside the group; else the gro
 // agents] in shared memory, by the thread group g.  grid_e: (G,G,2) f32, pos_e: (A,2) u8 of this env.
 // Preconditions: grid_e zero-filled or being zero-filled (see ZeroOwn / ZeroFiller), sm.table all zero, sm.lut filled
 // (raster_lut_fill) and pts visible (a barrier since).  Postcondition: sm.table all zero again, after a group barrier.
-// Phase 0 splits the group: warp 0's first lane walks the sequential mean while the other warps run overlap_fn() (the
-// caller's work that only needs pts, e.g. the write-back of the state) and bin every point's y (the y edges do not
-// depend on the mean) and fill the grid-value table.  early_release_fn() is called by every thread once it has read its
-// last point from pts (the step kernel hands the buffer back to the force group there).
+// overlap_fn(tid, n) is the caller's work that only needs pts (e.g. the write-back of the state); early_release_fn() is
+// called by every thread once it has read its last point from pts (the step kernel hands the buffer back to the force
+// group there).
+//
+// The window's centre is np.mean(vstack([x, xa]), axis=0)[0]: a plain left-to-right FP64 sum, i.e. a chain of N+A dependent
+// DADDs on ONE thread (23 cycles each: 3 us at N = 256, the longest single piece of an env's rasterisation).  The chain is
+// only needed when some point sits so close to a bin edge that the last bits of the mean decide its bin.  So every
+// thread first bins its points against a PARALLEL mean (tree sum; it differs from numpy's sequential one by at most
+// (N+A) 2^-52 max|x|) and checks that each point is further from the nearest edge than everything that could separate
+// the two computations (tol below, a rigorous bound with slack).  If all points pass, the bins -- hence the whole
+// observation -- are provably the ones numpy's edges give, and the chain is never walked; if any point fails (or EXACT:
+// the standalone rasteriser, which also reports the box) thread 0 walks the chain and the x bins are taken again against
+// numpy's exact edges.
 struct NoRelease { __device__ __forceinline__ void operator()() const {} };
 struct NoOverlap { __device__ __forceinline__ void operator()(int, int) const {} };
 
-template <bool SPLIT, typename Group, typename Zero, typename Release, typename Overlap>
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+#ifndef SWARM_SPEC_MEAN
+#define SWARM_SPEC_MEAN 1
+#endif
+template <bool EXACT, typename Group, typename Zero, typename Release, typename Overlap>
 __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __restrict__ pts, const KP& kp, const Group& g,
                                            float* __restrict__ grid_e, uint8_t* __restrict__ pos_e, const bool tma,
                                            const Zero zero, const Release early_release_fn, const Overlap overlap_fn,
@@ -1082,58 +1144,103 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_RASTER);
     const double lo_y = 0.0, hi_y = kp.y_hi;
     const double step_y = kp.step_y, inv_y = kp.inv_y;
-    // phase 0.  SPLIT (the latency-bound single-wave shape): the y bins are taken under the mean chain.  Otherwise (the
-    // throughput-bound shapes, where every extra instruction of the rasteriser is taken from a force warp): x and y
-    // are binned together after the mean.
-    const bool split = SPLIT && g.n > 32;
-    if (g.tid == 0) {
-        // np.mean(vstack([x,xa]),axis=0)[0] is a plain left-to-right FP64 sum: one dependent DADD per element
-        double s = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < P; ++i) s = __dadd_rn(s, pts[i].x);
-        sm.box[0] = div_by_const(s, (double)P, kp.inv_P);
-        trace_mark(kp, trace_rec, TR_MEAN);
-    }
-    if (!split || g.tid >= 32) {
-        const int w_tid = split ? g.tid - 32 : g.tid, w_n = split ? g.n - 32 : g.n;
-        if (!split) __syncwarp();
-        overlap_fn(w_tid, w_n);
-        if (SPLIT)
-            for (int p = w_tid; p < P; p += w_n) sm.cid[p] = count_le(pts[p].y, lo_y, hi_y, step_y, inv_y, G);
+    constexpr bool SPEC = !EXACT && SWARM_SPEC_MEAN;
+    int* const unsure = reinterpret_cast<int*>(sm.rred + 2 * kMaxWarps);
+    overlap_fn(g.tid, g.n);
+    if constexpr (SPEC) {
+        // phase 0: the parallel mean and the largest |x| (for the error bound)
+        double part = 0.0, amax = 0.0;
+        for (int p = g.tid; p < P; p += g.n) {
+            const double v = pts[p].x;
+            part += v;
+            amax = fmax(amax, fabs(v));
+        }
+        part = warp_sum(part);
+        amax = warp_max(amax);
+        if ((g.tid & 31) == 0) {
+            sm.rred[2 * (g.tid >> 5)] = part;
+            sm.rred[2 * (g.tid >> 5) + 1] = amax;
+        }
+        if (g.tid == 0) *unsure = 0;
+        g.sync();
+        double tot = 0.0, xmax = 0.0;
+        for (int w = 0; w < (g.n >> 5); ++w) {
+            tot += sm.rred[2 * w];
+            xmax = fmax(xmax, sm.rred[2 * w + 1]);
+        }
+        if (g.tid == 0) trace_mark(kp, trace_rec, TR_MEAN);
+        // Distance, in bins, that the guess q~ = (x - lo~) G/W can be from the point's position between numpy's edges
+        // e[i] = fl(fl(i step) + lo):  the two means differ by <= (P + 1) 2^-52 xmax (both sums carry <= (P-1) 2^-53 sum|x|,
+        // quotient / reciprocal-multiply roundings), lo, hi, step and each edge add a few ulp of (xmax + W), the guess's
+        // own subtraction and multiply another few ulp.  (P + 16) xmax + 16 W covers all of it; twice that, plus 1e-9.
+        const double lo_s = tot * kp.inv_P - kp.half_w;
+        const double tol = 1e-9 + 2.0 * ((double)(P + 16) * xmax + 32.0 * kp.half_w) * 2.220446049250313e-16 * kp.inv_x;
+        bool bad = !(tol < 0.25);       // (absurd magnitudes, NaN)
+        for (int p = g.tid; p < P; p += g.n) {
+            const double2 q = pts[p];
+            const int cy = count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
+            const double qs = (q.x - lo_s) * kp.inv_x;
+            const double fl = floor(qs);
+            const double fr = qs - fl;
+            bad |= !(fr > tol && fr < 1.0 - tol);          // next to an edge (q.x == hi_x included), or NaN
+            const int cx = (int)fmin(fmax(fl, -1.0), (double)G) + 1;    // #{edges <= x}: 0 left of the box, G + 1 right of it
+            if (p >= N) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
+                pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
+                pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
+            }
+            const int by = (q.y == hi_y) ? cy - 2 : cy - 1;             // histogramdd right-edge fix-up
+            sm.cid[p] = cx | ((by + 1) << 16);                          // bin + 1 in both halves
+        }
+        if (bad) *unsure = 1;
     }
     zero.before_table(g);
-    // phase 1: bin every point's x in FP64 against numpy's edges, count with warp-aggregated atomics
-    const double m = sm.box[0];
-    const double lo_x = m - kp.half_w, hi_x = m + kp.half_w;
-    const double step_x = div_by_const(hi_x - lo_x, (double)G, kp.inv_G);
-    // 1 / step_x seeds the bin guess: two Newton steps from the host's G / WIDTH (step_x differs from WIDTH / G by
-    // the rounding of mean +- WIDTH/2 only), a real division when the window sits absurdly far out
-    double inv_x = kp.inv_x;
-    const double dev = __fma_rn(-step_x, inv_x, 1.0);
-    if (fabs(dev) < 1e-4) {
-        inv_x = __fma_rn(inv_x, dev, inv_x);
-        inv_x = __fma_rn(inv_x, __fma_rn(-step_x, inv_x, 1.0), inv_x);
-    } else {
-        inv_x = 1.0 / step_x;
+    if (!SPEC || *unsure) {
+        if (g.tid == 0) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < P; ++i) s = __dadd_rn(s, pts[i].x);
+            sm.box[0] = div_by_const(s, (double)P, kp.inv_P);
+        }
+        g.sync();
+        // bin every point's x in FP64 against numpy's edges
+        const double m = sm.box[0];
+        const double lo_x = m - kp.half_w, hi_x = m + kp.half_w;
+        const double step_x = div_by_const(hi_x - lo_x, (double)G, kp.inv_G);
+        // 1 / step_x seeds the bin guess: two Newton steps from the host's G / WIDTH (step_x differs from WIDTH / G by
+        // the rounding of mean +- WIDTH/2 only), a real division when the window sits absurdly far out
+        double inv_x = kp.inv_x;
+        const double dev = __fma_rn(-step_x, inv_x, 1.0);
+        if (fabs(dev) < 1e-4) {
+            inv_x = __fma_rn(inv_x, dev, inv_x);
+            inv_x = __fma_rn(inv_x, __fma_rn(-step_x, inv_x, 1.0), inv_x);
+        } else {
+            inv_x = 1.0 / step_x;
+        }
+        for (int p = g.tid; p < P; p += g.n) {
+            const double2 q = pts[p];
+            const int cx = count_le(q.x, lo_x, hi_x, step_x, inv_x, G);
+            const int cy = count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
+            if (p >= N) {
+                pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
+                pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
+            }
+            const int bx = (q.x == hi_x) ? cx - 2 : cx - 1;
+            const int by = (q.y == hi_y) ? cy - 2 : cy - 1;
+            sm.cid[p] = (bx + 1) | ((by + 1) << 16);
+        }
     }
+    early_release_fn();
+    // phase 1: count with warp-aggregated atomics
     for (int base = 0; base < P; base += g.n) {
         const int p = base + g.tid;
         uint32_t key = 0xffffffffu;
         int cell = 0;
         if (p < P) {
-            const bool agent = p >= N;
-            const double2 q = pts[p];
-            const int cx = count_le(q.x, lo_x, hi_x, step_x, inv_x, G);
-            const int cy = SPLIT ? sm.cid[p] : count_le(q.y, lo_y, hi_y, step_y, inv_y, G);
-            if (agent) {   // np.digitize -> bin+1, clamped to G-1 (state_processors.py:35-40)
-                pos_e[2 * (p - N) + 0] = (uint8_t)(cx < G - 1 ? cx : G - 1);
-                pos_e[2 * (p - N) + 1] = (uint8_t)(cy < G - 1 ? cy : G - 1);
-            }
-            const int bx = (q.x == hi_x) ? cx - 2 : cx - 1;   // histogramdd right-edge fix-up
-            const int by = (q.y == hi_y) ? cy - 2 : cy - 1;
+            const int packed = sm.cid[p];
+            const int bx = (packed & 0xffff) - 1, by = (packed >> 16) - 1;
             if (bx >= 0 && bx < G && by >= 0 && by < G) {
                 cell = bx * G + by;
-                key = ((uint32_t)cell << 1) | (agent ? 1u : 0u);
+                key = ((uint32_t)cell << 1) | (p >= N ? 1u : 0u);
             }
         }
         const uint32_t peers = __match_any_sync(kFull, key);
@@ -1151,7 +1258,6 @@ __device__ __forceinline__ void env_raster(const Smem& sm, const double2* __rest
         }
         if (p < P) sm.cid[p] = mine;
     }
-    early_release_fn();
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_BINNED);
     zero.before_scatter(g);
     if (g.tid == 0) trace_mark(kp, trace_rec, TR_ZEROS);

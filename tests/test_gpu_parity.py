@@ -299,6 +299,47 @@ def test_rasterizer_edge_cases_through_state_processor(pkg):
         assert proc.positions.dtype == np.uint8 and np.array_equal(proc.positions, d["pos_%d" % k]), k
 
 
+def test_rasterizer_verified_parallel_mean_next_to_edges(M):
+    """The rasteriser bins against a PARALLEL mean and walks numpy's sequential one only when some point is too close to
+    an edge for the parallel mean to be trusted (env_raster).  States with a locust / an agent ON one of numpy's own
+    edges (first, inner, last = the histogram's closed right edge), a few ulps beside it, and windows far from the
+    origin: without the box (verified parallel mean + fall-back) and with it (always sequential) vs the oracle."""
+    rs = np.random.RandomState(7)
+    G = 84
+    for N in (5, 64, 80, 256):
+        xs, xas = [], []
+        for trial in range(8):
+            x = rs.rand(N, 2) * [2.5, 1.5] + [rs.uniform(-40.0, 40.0) * (trial % 3), 0.0]
+            xa = rs.rand(10, 2) * [3.4, 3.0] + [x[:, 0].mean() - 1.7, 0.0]
+            j, i = rs.randint(N), (0, G, rs.randint(1, G))[trial % 3]
+            k = rs.randint(10)
+            for _ in range(40):          # fixed point: the window moves with the point that is put on its edge
+                m = so.sequential_mean_x(x, xa)
+                edges = np.linspace(m - 1.5, m + 1.5, G + 1)
+                x[j, 0] = edges[i]
+                if trial >= 4:
+                    xa[k, 0] = edges[(i * 7 + 3) % (G + 1)]
+            for ulps in (0, 1, -1, 2, -3):
+                y, ya = x.copy(), xa.copy()
+                for _ in range(abs(ulps)):
+                    y[j, 0] = np.nextafter(y[j, 0], np.inf if ulps > 0 else -np.inf)
+                    ya[k, 0] = np.nextafter(ya[k, 0], -np.inf if ulps > 0 else np.inf)
+                xs.append(y); xas.append(ya)
+        xs, xas = np.stack(xs), np.stack(xas)
+        E = len(xs)
+        env = M.BatchedSwarmEnv(E, n_locusts=N)
+        env.x.copy_(to_dev(xs)); env.xa.copy_(to_dev(xas))
+        g1, p1 = env.observe()
+        g1, p1 = g1.cpu().numpy().copy(), p1.cpu().numpy().copy()
+        box = torch.zeros(E, 4, dtype=torch.float64, device="cuda")
+        g2, p2 = env.observe(box=box)
+        g2, p2 = g2.cpu().numpy(), p2.cpu().numpy()
+        for e in range(E):
+            go, po = so.rasterize(xs[e], xas[e], G)
+            assert np.array_equal(g1[e], go.astype(np.float32)) and np.array_equal(p1[e], po), (N, e)
+            assert np.array_equal(g2[e], go.astype(np.float32)) and np.array_equal(p2[e], po), (N, e)
+
+
 def test_fused_raster_equals_standalone_and_oracle(M):
     E, N = 64, 80
     env = M.BatchedSwarmEnv(E, n_locusts=N, seed=11)
