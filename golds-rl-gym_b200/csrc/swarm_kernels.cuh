@@ -283,21 +283,25 @@ __device__ __forceinline__ double div_by_const(const double a, const double b, c
 // one FMUL + one FFMA.  The dropped term is below 2^-24 -- the rounding of the result -- when eps rinv <= 2^-12, i.e. for
 // every pair further apart than 4096 eps (0.004 in the reference's units); closer pairs (a handful per reset, and the
 // ordered modes' self pair) take MUFU.RCP as before.  The choice depends on the pair alone, so every tiling and launch
-// shape still produces the same bits.
+// shape still produces the same bits.  Used where the pair loop is XU-bound (SERIES: MODE 3, the 64-wide super-tiles of
+// the large swarms: k_forces 144 -> 127 us at 4096 x 256); the small-swarm modes are not, and the extra branch costs them
+// more than the MUFU (measured: 4096 x 80 +13 %), so they keep it.
 #ifndef SWARM_RCP_SERIES
 #define SWARM_RCP_SERIES 1
 #endif
+template <bool SERIES>
 __device__ __forceinline__ float inv_r_eps(const float r, const float rinv, const float eps_s, const float ri_max) {
     float inv;
-#if SWARM_RCP_SERIES
-    inv = fmaf(-eps_s * rinv, rinv, rinv);
-    if (rinv > ri_max)
-#endif
+    if constexpr (SERIES && SWARM_RCP_SERIES) {
+        inv = fmaf(-eps_s * rinv, rinv, rinv);
+        if (rinv > ri_max) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + eps_s));
+    } else {
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r + eps_s));
+    }
     return inv;
 }
 
-template <bool PRECISE>
+template <bool PRECISE, bool SERIES = false>
 __device__ __forceinline__ float pair_weight(const float dx, const float dy, const KP& kp) {
     if (PRECISE) {
         const float r = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
@@ -312,7 +316,7 @@ __device__ __forceinline__ float pair_weight(const float dx, const float dy, con
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-r));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(r * kp.nInvL));
         const float s = fmaf(kp.F, e2, -e1);
-        inv = inv_r_eps(r, rinv, kp.eps_s, kp.ri_max);
+        inv = inv_r_eps<SERIES>(r, rinv, kp.eps_s, kp.ri_max);
         return s * inv;
     }
 }
@@ -376,12 +380,12 @@ __device__ __forceinline__ void stage_locusts(const Smem& sm, const KP& kp, cons
 constexpr int kTileUnroll = 4;   // rotation steps unrolled together (x targets per lane = pair chains in flight)
 
 // one unordered pair: force of source q on target tg, and (REACT) its reaction on the source
-template <bool REACT, bool PRECISE>
+template <bool REACT, bool PRECISE, bool SERIES = false>
 __device__ __forceinline__ void pair_sym(const float4 q, const float4 tg, const KP& kp, float& ax, float& ay,
                                          float& bx, float& by) {
     const float dx = (q.x - tg.x) + (q.z - tg.z);
     const float dy = (q.y - tg.y) + (q.w - tg.w);
-    const float w = pair_weight<PRECISE>(dx, dy, kp);
+    const float w = pair_weight<PRECISE, SERIES>(dx, dy, kp);
     ax = fmaf(w, dx, ax);
     ay = fmaf(w, dy, ay);
     if (REACT) {
@@ -429,8 +433,9 @@ __device__ __forceinline__ PairConst2 make_pair_const2(const KP& kp) {
 }
 
 // inv_r_eps for two pairs at once: the same roundings, packed; the close-pair test is one FMNMX + FSETP for both.
+template <bool SERIES>
 __device__ __forceinline__ f32x2 inv_r_eps2(const f32x2 r, const float riA, const float riB, const PairConst2& c) {
-#if SWARM_RCP_SERIES
+  if constexpr (SERIES && SWARM_RCP_SERIES) {
     const f32x2 ri = pk2(riA, riB);
     f32x2 inv = fma2(mul2(c.neps2, ri), ri, ri);
     if (fmaxf(riA, riB) > c.ri_max) {
@@ -443,7 +448,7 @@ __device__ __forceinline__ f32x2 inv_r_eps2(const f32x2 r, const float riA, cons
         inv = pk2(iA, iB);
     }
     return inv;
-#else
+  } else {
     float pA, pB, iA, iB, ne, ne_;
     upk2(r, pA, pB);
     upk2(c.neps2, ne, ne_);
@@ -451,7 +456,7 @@ __device__ __forceinline__ f32x2 inv_r_eps2(const f32x2 r, const float riA, cons
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iA) : "f"(pA));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iB) : "f"(pB));
     return pk2(iA, iB);
-#endif
+  }
 }
 
 
@@ -515,7 +520,7 @@ __device__ __forceinline__ void tile_sym_dual(const float4* __restrict__ tl1, co
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2a) : "f"(ga));
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2b) : "f"(gb));
             const f32x2 ns = fma2(c.nF2, pk2(e2a, e2b), pk2(e1a, e1b));    // -(F e2 - e1)
-            const f32x2 nw = mul2(ns, inv_r_eps2(r, ria, rib, c));         // (-w_1, -w_2)
+            const f32x2 nw = mul2(ns, inv_r_eps2<false>(r, ria, rib, c));  // (-w_1, -w_2)
             float nwa, nwb;
             upk2(nw, nwa, nwb);
             const f32x2 nwa2 = pk2(nwa, nwa), nwb2 = pk2(nwb, nwb);
@@ -655,7 +660,7 @@ __device__ __forceinline__ void pair2_fast(const float4 q, const Targets2& t, co
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2A) : "f"(gA));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2B) : "f"(gB));
     const f32x2 ns = fma2(c.nF2, pk2(e2A, e2B), pk2(e1A, e1B));      // -(F e2 - e1)
-    const f32x2 nw = mul2(ns, inv_r_eps2(r, riA, riB, c));           // (-w_A, -w_B)
+    const f32x2 nw = mul2(ns, inv_r_eps2<true>(r, riA, riB, c));     // (-w_A, -w_B)
     float nwA, nwB;
     upk2(nw, nwA, nwB);
     const f32x2 nwA2 = pk2(nwA, nwA), nwB2 = pk2(nwB, nwB);
@@ -760,19 +765,19 @@ __device__ __forceinline__ void forces_sym64_tiles(const Smem& sm, const KP& kp,
         const int H = 2 * J + h;
         const float4* tl = S + H * 64 + lane;
         float bx = 0.f, by = 0.f;
-        if (p == 0) pair_sym<true, PRECISE>(tl[0], tgB, kp, aBx, aBy, bx, by);
+        if (p == 0) pair_sym<true, PRECISE, true>(tl[0], tgB, kp, aBx, aBy, bx, by);
         tile_sym2<PRECISE>(tl + first, n, tgA, tgB, kp, nxt, aAx, aAy, aBx, aBy, bx, by);
         int last = first + n - 1;                        // offset of the element whose reaction this lane holds
         if (p == 0) {
             float ux, uy;
-            pair_sym<false, PRECISE>(tl[16], tgA, kp, aAx, aAy, ux, uy);
+            pair_sym<false, PRECISE, true>(tl[16], tgA, kp, aAx, aAy, ux, uy);
         } else if (p == 1) {
             bx = __shfl_sync(kFull, bx, nxt);
             by = __shfl_sync(kFull, by, nxt);
             const float4 q = tl[16];
             float ux, uy;
-            pair_sym<true, PRECISE>(q, tgA, kp, aAx, aAy, bx, by);
-            pair_sym<false, PRECISE>(q, tgB, kp, aBx, aBy, ux, uy);
+            pair_sym<true, PRECISE, true>(q, tgA, kp, aAx, aAy, bx, by);
+            pair_sym<false, PRECISE, true>(q, tgB, kp, aBx, aBy, ux, uy);
             last = 16;
         }
         sm.slot[(H * nslots + o) * 32 + ((lane + last) & 31)] = make_float2(bx, by);
@@ -1060,7 +1065,8 @@ __device__ __forceinline__ void tma_zero_fill_wait_done() {
 // One-time clear of the counter table (afterwards env_raster leaves it clean).
 template <typename Group>
 __device__ __forceinline__ void raster_table_clear(const Smem& sm, int words, const Group& g) {
-    for (int i = g.tid; i < words; i += g.n) sm.table[i] = 0u;
+    uint4* t4 = reinterpret_cast<uint4*>(sm.table);      // (smem_table_bytes is a multiple of 16, the table 16-byte aligned)
+    for (int i = g.tid; i < (words >> 2); i += g.n) t4[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the TMA zero fill reads these zeros
 }
 

@@ -17,6 +17,7 @@ for s in sys.argv[1:]:
     parts = s.split(":")
     E, N = (int(v) for v in parts[0].split("x"))
     tuning = 0
+    raster = "noraster" not in parts[1:]
     for t in parts[1:]:
         tuning |= PLACE.get(t, 0)
     env = M.BatchedSwarmEnv(E, n_locusts=N, seed=1234, max_episode_steps=128, tuning=tuning, binding="ctypes")
@@ -24,16 +25,21 @@ for s in sys.argv[1:]:
     print("plan", env.plan())
     a = torch.randn(E, 10, 2, device="cuda").clamp(-0.7, 0.7).contiguous()
     for _ in range(6):
-        env.step(a)
+        env.step(a, rasterize=raster)
     buf = torch.zeros(2 * E * 32, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     lib.swarm_debug_trace(ctypes.c_void_p(buf.data_ptr()), buf.numel())
-    env.step(a)
+    env.step(a, rasterize=raster)
     torch.cuda.synchronize()
     lib.swarm_debug_trace(None, 0)
     t = buf.cpu().numpy().reshape(2 * E, 16, 2)
     gt = t[:, :, 0].astype(np.float64)
     t0 = gt[gt > 0].min()
+    life = (t[:E, 7, 0] - t[:E, 0, 0]).astype(np.float64)
+    ent = np.sort(t[:E, 0, 0].astype(np.float64) - t0)
+    print("== %s  CTA lifetime entry->stored: med %.0f p10 %.0f p90 %.0f ns; span %.0f ns; mean resident CTAs/SM %.2f; entries by 10%% quantile: %s" % (
+        s, np.median(life), np.percentile(life, 10), np.percentile(life, 90), (t[:E, 7, 0].max() - t0), life.sum() / (t[:E, 7, 0].max() - t0) / 148,
+        " ".join("%.0f" % ent[int(q * (E - 1) / 10)] for q in range(11))))
     print("== %s  (globaltimer ns since first entry; SM cycles between consecutive phases of the same record in [])" % s)
     for name, rows in (("step CTAs", t[:E]), ("follower envs", t[E:])):
         if not (rows[:, :, 0] > 0).any():
