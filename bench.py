@@ -542,9 +542,9 @@ def main():
         secondary = dict(secondary or {}, paac5=paac5)
 
     if rank == 0:
-        # MUFU per UNORDERED pair: rsq + 2 ex2 + rcp; the 64-wide-tile mode (force_mode 3: N = 64, 256, ...) takes 1/(r+eps) from
+        # MUFU per UNORDERED pair: rsq + 2 ex2 + rcp; the unordered-pair modes (force_mode 1 and 3: N <= 512) take 1/(r+eps) from
         # the rsq by a one-term series instead of the rcp (fast math): 3
-        mufu_pair = 3.0 if (m["plan"]["force_mode"] == 3 and args.math == "fast") else 4.0
+        mufu_pair = 3.0 if (m["plan"]["force_mode"] in (1, 3) and args.math == "fast") else 4.0
         xu_ach = 0.5 * mufu_pair * pairs_per_launch / (ms_step * 1e-3)
         e2e_val = E_total * N / (m["e2e_ms_per_step"] * 1e-3)
         out = {

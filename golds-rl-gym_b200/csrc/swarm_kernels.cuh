@@ -278,14 +278,13 @@ __device__ __forceinline__ double div_by_const(const double a, const double b, c
 // carries ~2^-24 RELATIVE error however close the two particles are (plain FP32 positions lose
 // the direction of close pairs, where s/(r+eps) is steepest).  Coincident points (and the self
 // pair of the ordered loop) have d = 0 exactly and contribute exactly 0.
-// 1 / (r + eps) from rinv ~ 1/r without a third trip to the XU pipe (the pipe that bounds the pair loop):
+// 1 / (r + eps) from rinv ~ 1/r without a third trip to the XU pipe (the busiest pipe of the pair loop):
 //   1/(r + eps) = rinv / (1 + eps rinv) = rinv - (eps rinv) rinv + O((eps/r)^2),
 // one FMUL + one FFMA.  The dropped term is below 2^-24 -- the rounding of the result -- when eps rinv <= 2^-12, i.e. for
-// every pair further apart than 4096 eps (0.004 in the reference's units); closer pairs (a handful per reset, and the
-// ordered modes' self pair) take MUFU.RCP as before.  The choice depends on the pair alone, so every tiling and launch
-// shape still produces the same bits.  Used where the pair loop is XU-bound (SERIES: MODE 3, the 64-wide super-tiles of
-// the large swarms: k_forces 144 -> 127 us at 4096 x 256); the small-swarm modes are not, and the extra branch costs them
-// more than the MUFU (measured: 4096 x 80 +13 %), so they keep it.
+// every pair further apart than 4096 eps (0.004 in the reference's units); closer pairs (a dense swarm of 256 holds 5-25
+// of them at any time) take MUFU.RCP as before.  Which of the two a pair gets depends on the pair alone, so every tiling
+// and launch shape still produces the same bits.  Used by the unordered-pair modes (MODE 3: k_forces 144 -> 124 us at
+// 4096 x 256; MODE 1: 1-2 %); the ordered modes (N > 512) keep the MUFU.
 #ifndef SWARM_RCP_SERIES
 #define SWARM_RCP_SERIES 1
 #endif
@@ -438,7 +437,9 @@ __device__ __forceinline__ f32x2 inv_r_eps2(const f32x2 r, const float riA, cons
   if constexpr (SERIES && SWARM_RCP_SERIES) {
     const f32x2 ri = pk2(riA, riB);
     f32x2 inv = fma2(mul2(c.neps2, ri), ri, ri);
-    if (fmaxf(riA, riB) > c.ri_max) {
+    // (warp-uniform test: a plain branch, no reconvergence point in the pair loop -- 2 % faster than the divergent form;
+    // every caller runs with all 32 lanes)
+    if (__any_sync(kFull, fmaxf(riA, riB) > c.ri_max)) {
         float rA, rB, iA, iB, ne, ne_;
         upk2(r, rA, rB);
         upk2(inv, iA, iB);
@@ -520,7 +521,7 @@ __device__ __forceinline__ void tile_sym_dual(const float4* __restrict__ tl1, co
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2a) : "f"(ga));
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2b) : "f"(gb));
             const f32x2 ns = fma2(c.nF2, pk2(e2a, e2b), pk2(e1a, e1b));    // -(F e2 - e1)
-            const f32x2 nw = mul2(ns, inv_r_eps2<false>(r, ria, rib, c));  // (-w_1, -w_2)
+            const f32x2 nw = mul2(ns, inv_r_eps2<true>(r, ria, rib, c));   // (-w_1, -w_2)
             float nwa, nwb;
             upk2(nw, nwa, nwb);
             const f32x2 nwa2 = pk2(nwa, nwa), nwb2 = pk2(nwb, nwb);

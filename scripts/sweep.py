@@ -75,8 +75,8 @@ def run(E, N, boundary, reps=5, **kw):
         f()
     out["us_forces"] = min(timed(f, 20) / 20 for _ in range(3)) * 1e3
     pairs = E * N * (N + 10)
-    mode3 = N <= 512 and (N + 31) // 32 * 32 == (N + 63) // 64 * 64      # 64-wide tiles: 3 MUFU per unordered pair, else 4
-    out["xu_frac_steady"] = (1.5 if mode3 else 2.0) * pairs / (out["us_steady"] * 1e-6) / (148 * 15.93 * 1965e6)
+    # unordered-pair modes (N <= 512): 3 MUFU per unordered pair, else 4
+    out["xu_frac_steady"] = (1.5 if N <= 512 else 2.0) * pairs / (out["us_steady"] * 1e-6) / (148 * 15.93 * 1965e6)
     out["locust_updates_per_s"] = E * N / (out["us_steady"] * 1e-6)
     return out
 
