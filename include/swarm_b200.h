@@ -182,7 +182,10 @@ void swarm_step_host_clear(void);
 /* SwarmStateProcessor.process_state (state_processors.py:25-42): grid + uint8 agent cells.
  * box: nullable (E,4) f64 = [lo_x, hi_x, lo_y, hi_y], i.e. _get_bounding_box (:25-27) of
  * vstack([x, xa]).  n_agents may be 0 here (then xa/positions may be NULL): the box/grid of a
- * bare point set, as tests/env_tests.py:39 uses _get_bounding_box(state[0]). */
+ * bare point set, as tests/env_tests.py:39 uses _get_bounding_box(state[0]).
+ * The observation is numpy's bit for bit either way; with a box the window's centre is always taken by numpy's
+ * sequential FP64 sum (the box reports it), without one -- and inside swarm_step -- by a parallel sum that is verified
+ * against a rigorous error bound and replaced by the sequential one only when a point sits within that bound of a bin edge. */
 int swarm_rasterize(const SwarmParams* p, const double* x, const double* xa,
                     float* grid, uint8_t* positions, double* box, swarm_stream_t stream);
 
