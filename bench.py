@@ -567,6 +567,11 @@ def main():
             "env_steps_per_sec": env_steps, "pairs_per_sec": env_steps * N * (N + A),
             "roofline": {"bound": "fp32", "kernel": "k_step (fused step" + (" + k_raster_follow" if m["plan"]["launches"] == 2 else " + rasterise") + ")",
                          "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         # the same with (a) only the steady-state steps (median 8-step replay: no episode boundary inside) and
+                         # (b) the pair work of the auto-resets counted too: every 128th step also runs the reset's 10
+                         # burn-in steps (multiagent.py:59-61) for every env, 138 force evaluations per 128 counted steps
+                         "frac_steady_state": pairs_per_launch * FLOPS_PER_PAIR / (m["replay8_ms_per_step"]["median"] * 1e-3) / 1e12 / fp32_peak,
+                         "frac_counting_reset_burn_in": achieved / fp32_peak * (128.0 + 10.0) / 128.0,
                          "traffic": ncu_traffic(args.workload) if world == 1 else None,
                          "xu_pipe": {"achieved_mufu_per_s": xu_ach, "peak_mufu_per_s": xu_peak, "frac": xu_ach / xu_peak,
                                      "mufu_per_unordered_pair": mufu_pair,
