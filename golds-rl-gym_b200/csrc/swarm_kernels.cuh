@@ -376,7 +376,10 @@ __device__ __forceinline__ void stage_locusts(const Smem& sm, const KP& kp, cons
     }
 }
 
-constexpr int kTileUnroll = 4;   // rotation steps unrolled together (x targets per lane = pair chains in flight)
+#ifndef SWARM_TILE_UNROLL
+#define SWARM_TILE_UNROLL 4
+#endif
+constexpr int kTileUnroll = SWARM_TILE_UNROLL;   // rotation steps unrolled together (x targets per lane = pair chains in flight)
 
 // one unordered pair: force of source q on target tg, and (REACT) its reaction on the source
 template <bool REACT, bool PRECISE, bool SERIES = false>
