@@ -543,7 +543,14 @@ int block_threads(int N, int mode) {
 
 // threads of the raster group riding along with the force group in k_step
 // measured: 64 raster threads beat 32 for small swarms (1024 x 64: 14.2 vs 17.6 us per step)
-int raster_threads(int N, int A) { return (N + A) <= 1024 ? 64 : 128; }
+// threads of the raster group that rides along in k_step (WARPS shape).  64 as a rule; 96 bin a small swarm's points in ONE
+// round (N + A <= 96) -- taken when the CTA stays small (a single force warp: N = 64) or the batch has fewer CTAs than SMs,
+// i.e. when the extra registers cost no resident CTA (measured, profiles/r02_shapes.md: 1024 x 64 13.1 -> 12.8 us,
+// 4096 x 64 46.7 -> 45.1, 32 x 80 9.75 -> 9.0; but 4096 x 80 48.1 -> 55.9 with its three force warps)
+int raster_threads(int N, int A, int nf, int E, int sms) {
+    if (N + A <= 96 && (nf <= 32 || E <= sms)) return 96;
+    return (N + A) <= 1024 ? 64 : 128;
+}
 
 // raster: 0 none, 1 raster group (own point buffer), 2 the force group rasterises
 size_t step_smem(const SwarmParams* p, int raster, int n_stage, int mode) {
@@ -920,7 +927,7 @@ int plan_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
         if (follow_per_sm * follow_threads * rf + nf * rs > 65536) follow_fits = false;
         if (rgrid > sms * follow_per_sm) rgrid = sms * follow_per_sm;
     }
-    const bool warps_fit = nf + raster_threads(N, A) <= kMaxThreads && step_smem(p, 1, 2, mode) <= kMaxSmem;
+    const bool warps_fit = nf + raster_threads(N, A, nf, E, sms) <= kMaxThreads && step_smem(p, 1, 2, mode) <= kMaxSmem;
     int place = RASTER_NONE;
     if (want_grid) {
         const int forced = (p->tuning >> 4) & 3;
@@ -953,7 +960,7 @@ int plan_step(const SwarmParams* p, const SwarmState* st, const SwarmStepIO* io,
     // ... as long as its 32 threads do not push the batch out of a single wave of CTAs (registers)
     out->filler = (self && ((p->grid_size * p->grid_size) & 7) == 0 && (reinterpret_cast<uintptr_t>(io->grid) & 15) == 0 &&
                    nf + 32 <= kMaxThreads && E <= (long long)sms * (65536 / (64 * (nf + 32)))) ? 1 : 0;
-    out->nt = nf + (warps ? raster_threads(N, A) : 0) + (out->filler ? 32 : 0);
+    out->nt = nf + (warps ? raster_threads(N, A, nf, E, sms) : 0) + (out->filler ? 32 : 0);
     out->kernel = step_kernel(mode, p->math_mode != 0, place);
     if ((rc = prep(out->kernel, out->smem))) return rc;
     int grid = 0;
