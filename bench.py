@@ -171,11 +171,19 @@ def run_reference(args, wl):
         return
     from oracle import cpu_baseline as cb
     N = wl["N"]
+    # One "step" of this arm = one pass of every host core over its own envs.  How many envs a core owns is sized from a
+    # one-env calibration so that the K timed steps take about 20 s in total (1..64 envs per core): a 0.2 s sample -- what
+    # 20 steps of one env per core would be -- measured anywhere between 2.7e5 and 4.9e5 on the same box.
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 3))
     if cb.reference_staged():
-        res = cb.time_reference(N, steps=args.steps, warmup=args.warmup, envs_per_proc=1)
+        t_env = cb.time_reference(N, steps=2, warmup=1, envs_per_proc=1, procs=1)["seconds"] / 2.0
+        per = int(max(1, min(64, round(20.0 / (steps * max(t_env, 1e-6))))))
+        res = cb.time_reference(N, steps=steps, warmup=warm, envs_per_proc=per)
         kind, what = "reference", "the UNMODIFIED reference (oracle/_ref: fed_gym SwarmEnv.step + SwarmStateProcessor.process_state)"
     else:
-        res = cb.time_port(N, steps=args.steps, warmup=args.warmup, envs_per_proc=2)
+        t_env = cb.time_port(N, steps=2, warmup=1, envs_per_proc=1, procs=1)["seconds"] / 2.0
+        per = int(max(2, min(64, round(20.0 / (steps * max(t_env, 1e-6))))))
+        res = cb.time_port(N, steps=steps, warmup=warm, envs_per_proc=per)
         kind, what = "port", "NumPy FP64 port (oracle/_ref not staged on this box)"
     value = res["env_steps_per_s"] * N
     unit = "locust-updates/s"
